@@ -1,0 +1,273 @@
+"""``bev_pool_v2`` — B200-native drop-in for the reference autograd op.
+
+Mirrors ``/root/reference/mmdet3d/ops/bev_pool_v2/bev_pool.py`` name for name:
+``QuickCumsumCuda`` (:11-83), ``bev_pool_v2`` (:86-92), ``TRTBEVPoolv2``
+(:95-142) keep their signatures, argument meaning, dtype normalisation and
+return shapes.  What changes is underneath:
+
+* forward: no 82 MB ``new_zeros`` (:27), no scalar kernel + 164 MB
+  ``permute().contiguous()`` (:91).  One CUDA kernel writes the dense voxel
+  tensor once, zeros included, already in ``(B,C,Z,Y,X)`` memory order.
+  ``QuickCumsumCuda.apply`` still *returns a (B,Z,Y,X,C)-shaped tensor* — it is a
+  permuted view of that memory — so ``bev_pool_v2``'s
+  ``permute(0,4,1,2,3).contiguous()`` is a no-op view, byte-identical result.
+* backward: no ``argsort`` / ``where`` host sync (:47-57), no 164 MB
+  ``out_grad.contiguous()`` (:69).  The inverse interval ordering is a cached
+  device-side plan; ``out_grad`` is read in whatever layout autograd hands over.
+
+All native work goes through the C ABI in ``include/fusionocc_b200.h``.  There
+is no CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import FO_LAYOUT_BCZYX, FO_LAYOUT_BZYXC
+
+__all__ = ['bev_pool_v2', 'TRTBEVPoolv2', 'QuickCumsumCuda', 'VoxelPoolPlan', 'build_plan',
+           'clear_plan_cache']
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError('fusionocc_b200.bev_pool_v2 runs on CUDA (sm_100a) tensors only; '
+                               f'got a {t.device} tensor. There is no CPU fallback.')
+        if t.device != dev:
+            raise RuntimeError(f'all tensors must be on one device, got {dev} and {t.device}')
+    return dev
+
+
+class VoxelPoolPlan:
+    """Device-side index over one set of (ranks_bev, interval_starts, interval_lengths, ranks_feat).
+
+    ``fwd`` lets the forward kernel own dense output tiles; ``bwd`` is the inverse
+    interval ordering (what bev_pool.py:47-57 recomputes with argsort every
+    backward).  Valid while the index tensors are unchanged — the reference's
+    ``accelerate=True`` contract (view_transformer.py:175-194).
+    """
+
+    def __init__(self, fwd: torch.Tensor, B: int, n_vox: int, n_points: int, n_intervals: int,
+                 counts_dev: Optional[torch.Tensor] = None):
+        self.fwd = fwd                      # uint8 plan buffer
+        self.bwd: Optional[torch.Tensor] = None
+        self.bwd_rows = -1
+        self.B, self.n_vox = B, n_vox
+        self.n_points, self.n_intervals = n_points, n_intervals     # capacities when counts_dev is set
+        self.counts_dev = counts_dev        # int32[4] {n_kept, n_intervals, 0, 0} or None
+
+    def n_intervals_dev_ptr(self):
+        if self.counts_dev is None:
+            return None
+        return ctypes.c_void_p(self.counts_dev.data_ptr() + 4)
+
+    def n_points_dev_ptr(self):
+        return None if self.counts_dev is None else ctypes.c_void_p(self.counts_dev.data_ptr())
+
+    def flags(self) -> int:
+        """Debug/test helper (synchronises): bit0 = unsorted interval voxels, bit1 = out of range."""
+        return int(self.fwd[:4].view(torch.int32).item())
+
+    def ensure_bwd(self, ranks_feat: torch.Tensor, n_feat_rows: int) -> torch.Tensor:
+        if self.bwd is None or self.bwd_rows != n_feat_rows:
+            lib = _cabi.load()
+            dev = ranks_feat.device
+            nbytes = lib.fo_bwd_plan_bytes(self.n_points, n_feat_rows)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _cabi.check(lib.fo_bwd_plan_build(_stream(dev), _p(ranks_feat), self.n_points,
+                                                  self.n_points_dev_ptr(), n_feat_rows, _p(buf), nbytes),
+                            'fo_bwd_plan_build')
+            self.bwd, self.bwd_rows = buf, n_feat_rows
+        return self.bwd
+
+
+def build_plan(ranks_bev: torch.Tensor, interval_starts: torch.Tensor, interval_lengths: torch.Tensor,
+               B: int, n_vox: int) -> VoxelPoolPlan:
+    """Build the forward plan for caller-supplied index tensors (int32, contiguous, CUDA)."""
+    lib = _cabi.load()
+    dev = _require_cuda(ranks_bev, interval_starts, interval_lengths)
+    n_points, n_intervals = ranks_bev.numel(), interval_lengths.numel()
+    nbytes = lib.fo_fwd_plan_bytes(B * n_vox, n_points)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_fwd_plan_build(_stream(dev), _p(ranks_bev), _p(interval_starts), _p(interval_lengths),
+                                          n_points, n_intervals, None, B, n_vox, _p(buf), nbytes),
+                    'fo_fwd_plan_build')
+    return VoxelPoolPlan(buf, B, n_vox, n_points, n_intervals)
+
+
+# ---------------------------------------------------------------------------------------------
+# Plan cache: callers that pass the SAME index tensor objects again (accelerate mode, TRT-style
+# precomputed ranks) skip the plan kernels.  Entries hold strong references to the tensors, so an
+# id()/data_ptr can never be recycled while cached, and compare torch's in-place version counters.
+# ---------------------------------------------------------------------------------------------
+_PLAN_CACHE: 'OrderedDict[tuple, tuple]' = OrderedDict()
+_PLAN_CACHE_SIZE = 8
+
+
+def clear_plan_cache() -> None:
+    _PLAN_CACHE.clear()
+
+
+def _cached_plan(rb, st, ln, rf, B, n_vox) -> VoxelPoolPlan:
+    key = (id(rb), id(st), id(ln), id(rf), B, n_vox)
+    ver = (rb._version, st._version, ln._version, rf._version, rb.data_ptr(), st.data_ptr(), ln.data_ptr())
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None and hit[1] == ver:
+        _PLAN_CACHE.move_to_end(key)
+        return hit[0]
+    plan = build_plan(rb, st, ln, B, n_vox)
+    _PLAN_CACHE[key] = (plan, ver, (rb, st, ln, rf))
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+# ---------------------------------------------------------------------------------------------
+# Native calls
+# ---------------------------------------------------------------------------------------------
+def native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                   bev_feat_shape: Sequence[int], plan: VoxelPoolPlan,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Launch the forward; returns the fp32 contiguous (B,C,Z,Y,X) tensor."""
+    lib = _cabi.load()
+    B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
+    dev = depth.device
+    if out is None:
+        out = torch.empty((B, C, Z, Y, X), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_bev_pool_v2_forward(
+            _stream(dev), C, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat), _p(ranks_bev),
+            _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals, plan.n_intervals_dev_ptr(),
+            B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward')
+    return out
+
+
+def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                    interval_lengths, bev_feat_shape, plan: VoxelPoolPlan) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _cabi.load()
+    B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
+    dev = depth.device
+    n_feat_rows = feat.numel() // C
+    bwd = plan.ensure_bwd(ranks_feat, n_feat_rows)
+    depth_grad = torch.empty_like(depth)
+    feat_grad = torch.empty_like(feat)
+    sbytes = lib.fo_bwd_scratch_bytes(plan.n_intervals, C, og_layout)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_bev_pool_v2_backward(
+            _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat),
+            _p(ranks_bev), _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals,
+            _p(plan.counts_dev), B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad), _p(feat_grad),
+            _p(plan.fwd), plan.fwd.numel(), _p(bwd), bwd.numel(), _p(scratch), sbytes), 'fo_bev_pool_v2_backward')
+    return depth_grad, feat_grad
+
+
+def _classify_out_grad(out_grad: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """out_grad is the gradient of the (B,Z,Y,X,C)-shaped view.  Pick the layout it already has."""
+    if out_grad.dtype != torch.float32:
+        out_grad = out_grad.float()
+    if out_grad.permute(0, 4, 1, 2, 3).is_contiguous():
+        return out_grad, FO_LAYOUT_BCZYX            # gradient of bev_pool_v2()'s contiguous output
+    if out_grad.is_contiguous():
+        return out_grad, FO_LAYOUT_BZYXC            # channels-last upstream
+    # arbitrary strides: one copy into the native (B,C,Z,Y,X) order
+    return out_grad.permute(0, 4, 1, 2, 3).contiguous().permute(0, 2, 3, 4, 1), FO_LAYOUT_BCZYX
+
+
+class QuickCumsumCuda(torch.autograd.Function):
+    r"""BEVPoolv2 (https://arxiv.org/abs/2211.17111) — same contract as the reference class
+    (bev_pool.py:11-83): returns an fp32 tensor of shape ``bev_feat_shape = (B,Z,Y,X,C)``;
+    differentiable w.r.t. ``depth`` and ``feat`` only."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                interval_lengths, plan: Optional[VoxelPoolPlan] = None):
+        _require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
+        # dtype / contiguity normalisation exactly as bev_pool.py:19-25
+        ranks_bev = ranks_bev.int().contiguous()
+        depth = depth.contiguous().float()
+        feat = feat.contiguous().float()
+        ranks_depth = ranks_depth.contiguous().int()
+        ranks_feat = ranks_feat.contiguous().int()
+        interval_lengths = interval_lengths.contiguous().int()
+        interval_starts = interval_starts.contiguous().int()
+        shape = tuple(int(s) for s in bev_feat_shape)
+        if len(shape) != 5:
+            raise ValueError(f'bev_feat_shape must be (B,Z,Y,X,C), got {bev_feat_shape}')
+        B, Z, Y, X, C = shape
+        if feat.shape[-1] != C:
+            raise ValueError(f'feat has {feat.shape[-1]} channels but bev_feat_shape says {C}')
+        if plan is None:
+            plan = _cached_plan(ranks_bev, interval_starts, interval_lengths, ranks_feat, B, Z * Y * X)
+        out = native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                             shape, plan)
+        ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts, interval_lengths)
+        ctx.plan = plan
+        ctx.bev_feat_shape = shape
+        # (B,Z,Y,X,C)-shaped view of (B,C,Z,Y,X) memory: the wrapper's permute+contiguous is then free
+        return out.permute(0, 2, 3, 4, 1)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts, interval_lengths = ctx.saved_tensors
+        out_grad, layout = _classify_out_grad(out_grad)
+        depth_grad, feat_grad = native_backward(out_grad, layout, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                                                interval_starts, interval_lengths, ctx.bev_feat_shape, ctx.plan)
+        return depth_grad, feat_grad, None, None, None, None, None, None, None
+
+
+def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                interval_lengths):
+    """Drop-in for bev_pool.py:86-92.  Returns fp32 contiguous ``(B,C,Z,Y,X)``."""
+    x = QuickCumsumCuda.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                              interval_lengths)
+    x = x.permute(0, 4, 1, 2, 3).contiguous()        # already contiguous: no copy
+    return x
+
+
+def bev_pool_v2_with_plan(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                          interval_lengths, plan: VoxelPoolPlan):
+    """Same as :func:`bev_pool_v2` with an explicit, caller-owned plan (used by the view transformer,
+    whose rank precompute produces the plan for free)."""
+    x = QuickCumsumCuda.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                              interval_lengths, plan)
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+class TRTBEVPoolv2(torch.autograd.Function):
+    """Mirror of bev_pool.py:95-142: ONNX symbolic ``mmdeploy::bev_pool_v2`` and the eager
+    forward that unsqueezes the batch, pools with Z=1 and returns ``(B,Y,X,C)``."""
+
+    @staticmethod
+    def symbolic(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                 out_height=128, out_width=128):
+        return g.op('mmdeploy::bev_pool_v2', depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                    interval_lengths, out_height_i=out_height, out_width_i=out_width)
+
+    @staticmethod
+    def forward(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                out_height=128, out_width=128):
+        feat = feat.unsqueeze(0)
+        depth = depth.unsqueeze(0)
+        bev_feat_shape = (depth.shape[0], 1, out_height, out_width, feat.shape[-1])    # (B, Z, Y, X, C)
+        bev_feat = bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                               interval_lengths)
+        bev_feat = bev_feat.squeeze(2)
+        bev_feat = bev_feat.permute(0, 2, 3, 1)
+        return bev_feat

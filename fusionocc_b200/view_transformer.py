@@ -1,0 +1,269 @@
+"""``LSSViewTransformer`` — host-side mirror of the reference view transformer for the
+camera->voxel path, with the rank precompute and the splat on the B200-native library.
+
+Mirrors ``/root/reference/projects/FusionOcc/fusionocc/necks/view_transformer.py:37-340``
+(identical copies: ``mmdet3d/models/necks/view_transformer.py``, TEOcc, LiCROcc/FlashOcc,
+STCOcc): same constructor arguments, attribute names (``grid_lower_bound``,
+``grid_interval``, ``grid_size``, ``frustum``, ``D``, ``ranks_*``, ``interval_*``,
+``initial_flag`` ...), method names, argument lists and return tuples, including the
+five-``None`` empty case (:257-258, :274-275) and the dummy-zeros quirk (:200-210).
+
+What runs underneath
+  create_grid_infos / create_frustum   same torch CPU ops as the reference (init-time only)
+  get_lidar_coor                       same torch ops as the reference (same library kernels =>
+                                       same fp32 bits on the same device)
+  voxel_pooling_prepare_v2             ONE native call (fo_rank_prepare: voxelise+count, scan,
+                                       place, order) instead of ~50 eager launches and >= 4 host
+                                       syncs; one 16-byte read-back sizes the returned tensors
+  voxel_pooling_v2 / view_transform    rank precompute + forward splat; with ``sync_free=True`` no
+                                       host sync at all (counts stay on the device)
+
+The mm* base class / registry are optional: when mmengine / mmdet3d are importable the class
+derives from ``BaseModule`` and registers itself under the reference's name; otherwise it is a
+plain ``nn.Module`` (mmcv/mmengine/mmdet are not installable in the build image).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .bev_pool import (VoxelPoolPlan, _PLAN_CACHE, _PLAN_CACHE_SIZE, _p, _stream, bev_pool_v2,
+                       bev_pool_v2_with_plan)
+
+try:  # optional mm* integration
+    from mmengine.model import BaseModule as _Base          # type: ignore
+except Exception:  # noqa: BLE001
+    _Base = nn.Module
+
+__all__ = ['LSSViewTransformer', 'rank_prepare']
+
+
+def rank_prepare(coor: torch.Tensor, grid_lower_bound, grid_interval, grid_size_xyz
+                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                            torch.Tensor, VoxelPoolPlan]:
+    """Native rank precompute (fo_rank_prepare).  No host sync.
+
+    Returns capacity-sized int32 buffers ``(ranks_bev, ranks_depth, ranks_feat, interval_starts,
+    interval_lengths, counts_dev, plan)``; the live sizes are ``counts_dev[0]`` (kept points) and
+    ``counts_dev[1]`` (intervals), on the device.
+    """
+    if not coor.is_cuda:
+        raise RuntimeError('fusionocc_b200 rank precompute runs on CUDA tensors only (no CPU fallback)')
+    lib = _cabi.load()
+    B, N, D, H, W, three = coor.shape
+    assert three == 3
+    coor = coor.contiguous().float()
+    X, Y, Z = (int(v) for v in grid_size_xyz)
+    dev = coor.device
+    P = B * N * D * H * W
+    NV = B * X * Y * Z
+    cap_iv = min(P, NV)
+    i32 = dict(dtype=torch.int32, device=dev)
+    ranks_bev = torch.empty(P, **i32)
+    ranks_depth = torch.empty(P, **i32)
+    ranks_feat = torch.empty(P, **i32)
+    starts = torch.empty(cap_iv, **i32)
+    lengths = torch.empty(cap_iv, **i32)
+    counts = torch.empty(4, **i32)
+    plan_bytes = lib.fo_fwd_plan_bytes(NV, P)
+    plan_buf = torch.empty(plan_bytes, dtype=torch.uint8, device=dev)
+    sbytes = lib.fo_rank_prepare_scratch_bytes(P, NV)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_rank_prepare(
+            _stream(dev), _p(coor), B, N, D, H, W, _cabi.f3(grid_lower_bound), _cabi.f3(grid_interval),
+            X, Y, Z, _p(ranks_bev), _p(ranks_depth), _p(ranks_feat), _p(starts), _p(lengths), _p(counts),
+            _p(plan_buf), plan_bytes, _p(scratch), sbytes), 'fo_rank_prepare')
+    plan = VoxelPoolPlan(plan_buf, B, X * Y * Z, P, cap_iv, counts_dev=counts)
+    return ranks_bev, ranks_depth, ranks_feat, starts, lengths, counts, plan
+
+
+class LSSViewTransformer(_Base):
+    r"""Lift-Splat-Shoot view transformer with BEVPoolv2 (https://arxiv.org/abs/2008.05711,
+    https://arxiv.org/abs/2211.17111).  Arguments as in the reference (view_transformer.py:61-85).
+
+    Extra, opt-in argument: ``sync_free`` (default False) — ``voxel_pooling_v2`` skips the one
+    remaining host read-back; the all-filtered case then returns regular zeros of the normal output
+    shape instead of the reference's ``print`` + Z-collapsed dummy (:200-210).
+    """
+
+    def __init__(self, grid_config, input_size, downsample=16, in_channels=512, out_channels=64,
+                 accelerate=False, sid=False, collapse_z=True, sync_free=False):
+        super().__init__()
+        self.grid_config = grid_config
+        self.downsample = downsample
+        self.create_grid_infos(**grid_config)
+        self.sid = sid
+        self.frustum = self.create_frustum(grid_config['depth'], input_size, downsample)
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        self.depth_net = nn.Conv2d(in_channels, self.D + self.out_channels, kernel_size=1, padding=0)
+        self.accelerate = accelerate
+        self.initial_flag = True
+        self.collapse_z = collapse_z
+        self.sync_free = sync_free
+        self._accel_plan: Optional[VoxelPoolPlan] = None
+
+    # ------------------------------------------------------------------ a1 (:87-103)
+    def create_grid_infos(self, x, y, z, **kwargs):
+        self.grid_lower_bound = torch.Tensor([cfg[0] for cfg in [x, y, z]])
+        self.grid_interval = torch.Tensor([cfg[2] for cfg in [x, y, z]])
+        self.grid_size = torch.Tensor([(cfg[1] - cfg[0]) / cfg[2] for cfg in [x, y, z]])
+
+    # ------------------------------------------------------------------ a2 (:105-133)
+    def create_frustum(self, depth_cfg, input_size, downsample):
+        H_in, W_in = input_size
+        H_feat, W_feat = H_in // downsample, W_in // downsample
+        d = torch.arange(*depth_cfg, dtype=torch.float).view(-1, 1, 1).expand(-1, H_feat, W_feat)
+        self.D = d.shape[0]
+        if self.sid:
+            d_sid = torch.arange(self.D).float()
+            depth_cfg_t = torch.tensor(depth_cfg).float()
+            d_sid = torch.exp(torch.log(depth_cfg_t[0]) + d_sid / (self.D - 1) *
+                              torch.log((depth_cfg_t[1] - 1) / depth_cfg_t[0]))
+            d = d_sid.view(-1, 1, 1).expand(-1, H_feat, W_feat)
+        x = torch.linspace(0, W_in - 1, W_feat, dtype=torch.float).view(1, 1, W_feat).expand(self.D, H_feat, W_feat)
+        y = torch.linspace(0, H_in - 1, H_feat, dtype=torch.float).view(1, H_feat, 1).expand(self.D, H_feat, W_feat)
+        return torch.stack((x, y, d), -1)          # D x H x W x 3
+
+    def _frustum_on(self, like: torch.Tensor) -> torch.Tensor:
+        """``self.frustum.to(like)`` (:161) without re-uploading the template every forward."""
+        c = getattr(self, '_frustum_cache', None)
+        if c is None or c[0] is not self.frustum or c[1].device != like.device or c[1].dtype != like.dtype:
+            c = (self.frustum, self.frustum.to(like))
+            self._frustum_cache = c
+        return c[1]
+
+    # ------------------------------------------------------------------ a3 (:135-173)
+    def get_lidar_coor(self, sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
+        """Frustum points in the ego/lidar frame, (B, N, D, H, W, 3).  ``ego2global`` is unused, as in
+        the reference.  A 4x4 ``bda`` (STCOcc variant, bevdet_utils/view_transformer.py:202-203) adds
+        its translation."""
+        B, N, _, _ = sensor2ego.shape
+        points = self._frustum_on(sensor2ego) - post_trans.view(B, N, 1, 1, 1, 3)
+        points = torch.inverse(post_rots).view(B, N, 1, 1, 1, 3, 3).matmul(points.unsqueeze(-1))
+        points = torch.cat((points[..., :2, :] * points[..., 2:3, :], points[..., 2:3, :]), 5)
+        combine = sensor2ego[:, :, :3, :3].matmul(torch.inverse(cam2imgs[:, :, :3, :3]))
+        points = combine.view(B, N, 1, 1, 1, 3, 3).matmul(points).squeeze(-1)
+        points += sensor2ego[:, :, :3, 3].view(B, N, 1, 1, 1, 3)
+        points = bda[:, :3, :3].reshape(B, 1, 1, 1, 1, 3, 3).matmul(points.unsqueeze(-1)).squeeze(-1)
+        if bda.shape[-1] == 4:
+            points = points + bda[:, :3, 3].view(B, 1, 1, 1, 1, 3)
+        return points
+
+    # ------------------------------------------------------------------ a5 (:175-194)
+    def init_acceleration_v2(self, coor):
+        ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = \
+            self.voxel_pooling_prepare_v2(coor)
+        self.ranks_bev = ranks_bev.int().contiguous()
+        self.ranks_feat = ranks_feat.int().contiguous()
+        self.ranks_depth = ranks_depth.int().contiguous()
+        self.interval_starts = interval_starts.int().contiguous()
+        self.interval_lengths = interval_lengths.int().contiguous()
+
+    # ------------------------------------------------------------------ a4 (:223-281)
+    def _grid_xyz(self):
+        return int(self.grid_size[0]), int(self.grid_size[1]), int(self.grid_size[2])
+
+    def voxel_pooling_prepare_v2(self, coor):
+        """Rank precompute.  Same return contract as the reference: int32 contiguous
+        ``(ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths)`` sorted by
+        ``ranks_bev`` (ties in ascending point index), or five ``None`` when nothing survives."""
+        rb, rd, rf, st, ln, counts, plan = rank_prepare(coor, self.grid_lower_bound.tolist(),
+                                                        self.grid_interval.tolist(), self._grid_xyz())
+        n_kept, n_iv = (int(v) for v in counts[:2].tolist())           # the one host read-back
+        if n_kept == 0 or n_iv == 0:
+            return None, None, None, None, None
+        rb, rd, rf, st, ln = rb[:n_kept], rd[:n_kept], rf[:n_kept], st[:n_iv], ln[:n_iv]
+        # hand the plan to the op: a following bev_pool_v2(...) on these very tensors finds it cached
+        exact = VoxelPoolPlan(plan.fwd, plan.B, plan.n_vox, n_kept, n_iv)
+        key = (id(rb), id(st), id(ln), id(rf), plan.B, plan.n_vox)
+        ver = (rb._version, st._version, ln._version, rf._version, rb.data_ptr(), st.data_ptr(), ln.data_ptr())
+        _PLAN_CACHE[key] = (exact, ver, (rb, st, ln, rf))
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
+        return rb, rd, rf, st, ln
+
+    # ------------------------------------------------------------------ a6 (:196-221)
+    def voxel_pooling_v2(self, coor, depth, feat):
+        X, Y, Z = self._grid_xyz()
+        if self.sync_free:
+            rb, rd, rf, st, ln, counts, plan = rank_prepare(coor, self.grid_lower_bound.tolist(),
+                                                            self.grid_interval.tolist(), (X, Y, Z))
+            feat = feat.permute(0, 1, 3, 4, 2)
+            bev_feat_shape = (depth.shape[0], Z, Y, X, feat.shape[-1])
+            bev_feat = bev_pool_v2_with_plan(depth, feat, rd, rf, rb, bev_feat_shape, st, ln, plan)
+        else:
+            ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = \
+                self.voxel_pooling_prepare_v2(coor)
+            if ranks_feat is None:
+                print('warning ---> no points within the predefined bev receptive field')
+                dummy = torch.zeros(size=[feat.shape[0], feat.shape[2], Z, X, Y]).to(feat)
+                dummy = torch.cat(dummy.unbind(dim=2), 1)
+                return dummy
+            feat = feat.permute(0, 1, 3, 4, 2)
+            bev_feat_shape = (depth.shape[0], Z, Y, X, feat.shape[-1])          # (B, Z, Y, X, C)
+            bev_feat = bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape,
+                                   interval_starts, interval_lengths)
+        if self.collapse_z:
+            bev_feat = torch.cat(bev_feat.unbind(dim=2), 1)
+        return bev_feat
+
+    # ------------------------------------------------------------------ (:283-316)
+    def pre_compute(self, input):
+        if self.initial_flag:
+            coor = self.get_lidar_coor(*input[1:7])
+            self.init_acceleration_v2(coor)
+            self.initial_flag = False
+
+    def view_transform_core(self, input, depth, tran_feat):
+        B, N, C, H, W = input[0].shape
+        if self.accelerate:
+            feat = tran_feat.view(B, N, self.out_channels, H, W)
+            feat = feat.permute(0, 1, 3, 4, 2)
+            depth = depth.view(B, N, self.D, H, W)
+            X, Y, Z = self._grid_xyz()
+            bev_feat_shape = (depth.shape[0], Z, Y, X, feat.shape[-1])          # (B, Z, Y, X, C)
+            bev_feat = bev_pool_v2(depth, feat, self.ranks_depth, self.ranks_feat, self.ranks_bev,
+                                   bev_feat_shape, self.interval_starts, self.interval_lengths)
+            bev_feat = bev_feat.squeeze(2)
+        else:
+            coor = self.get_lidar_coor(*input[1:7])
+            bev_feat = self.voxel_pooling_v2(coor, depth.view(B, N, self.D, H, W),
+                                             tran_feat.view(B, N, self.out_channels, H, W))
+        return bev_feat, depth
+
+    def view_transform(self, input, depth, tran_feat):
+        if self.accelerate:
+            self.pre_compute(input)
+        return self.view_transform_core(input, depth, tran_feat)
+
+    def forward(self, input):
+        """input = [x(B,N,C,H,W), sensor2ego, ego2global, cam2img, post_rots, post_trans, bda, ...]"""
+        x = input[0]
+        B, N, C, H, W = x.shape
+        x = x.view(B * N, C, H, W)
+        x = self.depth_net(x)
+        depth_digit = x[:, :self.D, ...]
+        tran_feat = x[:, self.D:self.D + self.out_channels, ...]
+        depth = depth_digit.softmax(dim=1)
+        return self.view_transform(input, depth, tran_feat)
+
+    def get_mlp_input(self, rot, tran, intrin, post_rot, post_tran, bda):
+        return None
+
+
+def _try_register():
+    """Register under the reference's registry name when mmdet3d's registry is importable."""
+    try:
+        from mmdet3d.registry import MODELS  # type: ignore
+        if MODELS.get('LSSViewTransformer') is None:
+            MODELS.register_module(name='LSSViewTransformer', module=LSSViewTransformer)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+_try_register()

@@ -1,0 +1,210 @@
+/*
+ * fusionocc_b200 — C ABI of the B200-native camera->voxel view transformation
+ * (bev_pool_v2 forward / backward splat + the rank-precompute stage).
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device
+ * pointers, sizes and a CUDA stream; no torch / pybind types appear.  The
+ * library allocates nothing and frees nothing: all buffers (inputs, outputs and
+ * scratch) are owned by the caller, exactly like the reference extension, whose
+ * Python side allocates `out` / the gradients and lends raw pointers for the
+ * duration of one launch (reference: mmdet3d/ops/bev_pool_v2/bev_pool.py:27,67-68;
+ * src/bev_pool.cpp:40-56,86-103).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:7-9    void bev_pool_v2(int c, int n_intervals, ...)
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:11-14  void bev_pool_v2_grad(int c, int n_intervals, ...)
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:30-57  bev_pool_v2_forward  (pybind, at::Tensor)
+ *   mmdet3d/ops/bev_pool_v2/src/bev_pool.cpp:74-104 bev_pool_v2_backward (pybind, at::Tensor)
+ *   mmdet3d/ops/bev_pool_v2/bev_pool.py:47-57       backward re-sort + interval rebuild (torch ops)
+ *   mmdet3d/ops/bev_pool_v2/bev_pool.py:91          permute(0,4,1,2,3).contiguous()
+ *   projects/FusionOcc/fusionocc/necks/view_transformer.py:223-281  voxel_pooling_prepare_v2 (torch ops)
+ *
+ * Conventions
+ *   - All functions return FO_OK (0) or an FO_ERR_* code; fo_last_error() returns a
+ *     thread-local human-readable message for the last failure on this thread.
+ *   - All launches go to `stream` (a cudaStream_t passed as void*); nothing uses
+ *     the legacy default stream implicitly and nothing synchronises the host.
+ *   - Re-entrant: no global mutable state besides the thread-local error string.
+ *   - Index arrays are int32, values are fp32, like the reference extension.
+ *   - "ranks" arrays are sorted by ranks_bev (ties in ascending ranks_depth);
+ *     interval k covers positions [interval_starts[k], +interval_lengths[k]).
+ *
+ * Built for sm_100a only.  There is no CPU fallback.
+ */
+#ifndef FUSIONOCC_B200_H_
+#define FUSIONOCC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO_ABI_VERSION 1
+
+#define FO_OK                  0
+#define FO_ERR_INVALID_ARG     1   /* null pointer, negative size, bad enum, misaligned buffer   */
+#define FO_ERR_CUDA            2   /* a CUDA runtime call or launch failed (message has details) */
+#define FO_ERR_UNSUPPORTED     3   /* shape outside what the kernels implement                  */
+#define FO_ERR_SCRATCH         4   /* scratch / plan buffer smaller than fo_*_bytes() asked for */
+
+/* Memory layout of the dense voxel tensor (the forward output / the backward's out_grad). */
+#define FO_LAYOUT_BCZYX  0   /* contiguous (B,C,Z,Y,X): what bev_pool_v2() returns (bev_pool.py:91)      */
+#define FO_LAYOUT_BZYXC  1   /* contiguous (B,Z,Y,X,C): what the reference extension itself writes/reads */
+
+typedef void *fo_stream_t;   /* cudaStream_t */
+
+int         fo_abi_version(void);
+const char *fo_last_error(void);
+/* Compile-time facts, for logs and tests: "sm_100a", tile size, etc. */
+const char *fo_build_info(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward plan.  A small device-side index over the interval list that lets the forward kernel own
+ * dense output tiles: tile_first_interval[t] for every tile of FO_TILE_VOXELS consecutive voxels,
+ * a voxel-sortedness flag, and pos->interval ids for the backward.  Depends only on
+ * (ranks_bev, interval_starts, interval_lengths, B, Z*Y*X): build once and reuse while those are
+ * unchanged (the reference's `accelerate=True` caching, view_transformer.py:175-194), or rebuild per
+ * call (a few microseconds).
+ *
+ * n_intervals_dev: optional device pointer to the live interval count (int32).  When non-NULL the
+ * kernels read the count from there (sync-free pipelines) and `n_intervals` is only the capacity of
+ * the interval arrays; when NULL `n_intervals` is the count.
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_fwd_plan_bytes(int64_t n_voxels_total /* B*Z*Y*X */, int64_t n_points_capacity);
+
+int fo_fwd_plan_build(fo_stream_t stream,
+                      const int32_t *ranks_bev, const int32_t *interval_starts,
+                      const int32_t *interval_lengths,
+                      int64_t n_points, int64_t n_intervals, const int32_t *n_intervals_dev,
+                      int32_t B, int64_t n_voxels_per_sample /* Z*Y*X */,
+                      void *plan, size_t plan_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * bev_pool_v2 forward.  Replaces bev_pool.cpp:7-9 + the 82 MB new_zeros (bev_pool.py:27) + the
+ * permute copy (bev_pool.py:91): every element of `out` is written exactly once, zeros included, in
+ * `out_layout` order, with per-interval sequential FMA accumulation in interval order starting from
+ * +0.0f (bit-identical to bev_pool_cuda.cu:39-47).
+ *
+ *   depth        fp32 [n_depth]           flat (B,N,D,H,W), indexed by ranks_depth
+ *   feat         fp32 [n_feat_rows, c]    flat (B,N,H,W,C), rows indexed by ranks_feat
+ *   out          fp32 B*c*n_voxels_per_sample elements, layout `out_layout`
+ *   plan         from fo_fwd_plan_build for the same index arrays
+ * Interval voxels that are not strictly increasing, or ranks outside the grid, are detected by the
+ * plan; the call then takes the order-agnostic scatter path (same results for valid input).
+ * ------------------------------------------------------------------------------------------------ */
+int fo_bev_pool_v2_forward(fo_stream_t stream, int32_t c,
+                           const float *depth, const float *feat,
+                           const int32_t *ranks_depth, const int32_t *ranks_feat,
+                           const int32_t *ranks_bev,
+                           const int32_t *interval_starts, const int32_t *interval_lengths,
+                           int64_t n_points, int64_t n_intervals, const int32_t *n_intervals_dev,
+                           int32_t B, int64_t n_voxels_per_sample,
+                           float *out, int32_t out_layout,
+                           const void *plan, size_t plan_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward plan = the inverse interval ordering: forward positions regrouped by ranks_feat (stable),
+ * i.e. the arrays the reference rebuilds with argsort / where on every backward
+ * (bev_pool.py:47-57).  Depends only on ranks_feat; cache it with the forward plan.
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_bwd_plan_bytes(int64_t n_points_capacity, int64_t n_feat_rows);
+
+int fo_bwd_plan_build(fo_stream_t stream, const int32_t *ranks_feat,
+                      int64_t n_points, const int32_t *n_points_dev, int64_t n_feat_rows,
+                      void *plan, size_t plan_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * bev_pool_v2 backward.  Replaces bev_pool.py:44-83 + bev_pool.cpp:11-14: no re-sort, no
+ * out_grad.contiguous() copy, no atomics.  depth_grad / feat_grad are fully written (zeros where no
+ * point contributes).  depth_grad[p] = sum_c out_grad[v,c]*feat[q,c] sequentially over c;
+ * feat_grad[q,c] = sum_i out_grad[v_i,c]*depth[p_i] sequentially in (ranks_bev, position) order —
+ * the reference's orders, so both are bit-identical to bev_pool_cuda.cu:91-120.
+ *
+ *   out_grad     fp32, layout `og_layout` (FO_LAYOUT_BCZYX is the gradient of bev_pool_v2()'s output)
+ *   scratch      fo_bwd_scratch_bytes() bytes (compact gathered out_grad rows when og is BCZYX)
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_bwd_scratch_bytes(int64_t n_intervals_capacity, int32_t c, int32_t og_layout);
+
+int fo_bev_pool_v2_backward(fo_stream_t stream, int32_t c,
+                            const float *out_grad, int32_t og_layout,
+                            const float *depth, const float *feat,
+                            const int32_t *ranks_depth, const int32_t *ranks_feat,
+                            const int32_t *ranks_bev,
+                            const int32_t *interval_starts, const int32_t *interval_lengths,
+                            int64_t n_points, int64_t n_intervals, const int32_t *n_counts_dev,
+                            int32_t B, int64_t n_voxels_per_sample,
+                            int64_t n_depth, int64_t n_feat_rows,
+                            float *depth_grad, float *feat_grad,
+                            const void *fwd_plan, size_t fwd_plan_bytes,
+                            const void *bwd_plan, size_t bwd_plan_bytes,
+                            void *scratch, size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rank precompute.  Replaces view_transformer.py:223-281 (about 50 eager torch launches, >= 4 host
+ * syncs, a library sort) by: voxelise + count, one scan, placement, in-interval ordering.
+ *
+ *   coor         fp32 [B*N*D*H*W, 3] frustum points in ego space (get_lidar_coor output)
+ *   lower/interval  grid_lower_bound[3], grid_interval[3] (host floats; index = trunc((coor-lb)/itv),
+ *                IEEE sub then IEEE div, truncation toward zero, view_transformer.py:246-248)
+ *   grid X,Y,Z   integer grid size
+ * Outputs (capacity n_points_total each for ranks_*, min(n_points_total, B*Z*Y*X) for intervals):
+ *   ranks_bev / ranks_depth / ranks_feat / interval_starts / interval_lengths  int32
+ *   counts_dev   int32[4] on device: {n_kept, n_intervals, 0, 0}
+ *   fwd_plan     optional (may be NULL): filled as by fo_fwd_plan_build
+ * Integer arithmetic is exact (the reference's fp32 rank arithmetic is exact only for
+ * B*Z*Y*X < 2^24; above that the reference itself is wrong).
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total);
+
+int fo_rank_prepare(fo_stream_t stream, const float *coor,
+                    int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+                    const float lower_bound[3], const float interval[3],
+                    int32_t X, int32_t Y, int32_t Z,
+                    int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
+                    int32_t *interval_starts, int32_t *interval_lengths,
+                    int32_t *counts_dev,
+                    void *fwd_plan, size_t fwd_plan_bytes,
+                    void *scratch, size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Source-compatible L0 symbols.  Same C signatures, semantics (assign into a caller-zeroed
+ * (B,Z,Y,X,C) `out`; backward arrays already re-sorted by ranks_feat) and stream behaviour (legacy
+ * default stream) as the two launchers bev_pool.cpp declares at :7-14, so the reference's own
+ * bev_pool.cpp can be linked against this library unchanged.
+ * ------------------------------------------------------------------------------------------------ */
+void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth, const float *feat,
+                           const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
+                           const int *interval_starts, const int *interval_lengths, float *out);
+
+void fo_compat_bev_pool_v2_grad(int c, int n_intervals, const float *out_grad,
+                                const float *depth, const float *feat,
+                                const int *ranks_depth, const int *ranks_feat, const int *ranks_bev,
+                                const int *interval_starts, const int *interval_lengths,
+                                float *depth_grad, float *feat_grad);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry (end-to-end measurement and non-torch hosts): H2D of the inputs,
+ * rank precompute + forward (+ backward when out_grad_host != NULL), D2H of the results, all on
+ * `stream`, using a caller-provided device workspace.  Host buffers should be pinned.
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_view_transform_host_workspace_bytes(int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+                                              int32_t c, int32_t X, int32_t Y, int32_t Z,
+                                              int32_t with_backward);
+
+int fo_view_transform_host(fo_stream_t stream,
+                           const float *coor_host, const float *depth_host, const float *feat_host,
+                           const float *out_grad_host /* may be NULL: forward only */,
+                           int32_t B, int32_t N, int32_t D, int32_t H, int32_t W, int32_t c,
+                           const float lower_bound[3], const float interval[3],
+                           int32_t X, int32_t Y, int32_t Z,
+                           float *out_host /* (B,c,Z,Y,X) */,
+                           float *depth_grad_host, float *feat_grad_host,
+                           int32_t counts_host[4],
+                           void *workspace_dev, size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUSIONOCC_B200_H_ */
