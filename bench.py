@@ -1,0 +1,509 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--shape base|native|stress] [--batch B_PER_GPU]
+
+Metric: voxel-pool samples/s (and HBM GB/s of the dominant kernel vs the measured peak) for the
+FusionOcc camera->voxel view transformation at 6 cams 256x704 -> 16x44, D=88, C=32, grid 200x200x16.
+
+A "step" is one pass of the whole hot path over one batch of synthetic nuScenes-shaped input:
+    rank precompute (fo_rank_prepare)  ->  forward splat  ->  backward plan  ->  backward
+with B samples per GPU (default 8: the training shape, BASELINE.json configs[3]/[1]).  Nothing is
+cached across steps: every step re-derives ranks, intervals and both plans from `coor`.
+
+  value   samples/s over all GPUs with inputs resident in HBM (CUDA-event time, max over ranks)
+  e2e     the same step through the host-buffer C-ABI entry (fo_view_transform_host): pinned host
+          inputs (coor, depth, feat, out_grad) H2D and results (voxels, depth_grad, feat_grad) D2H
+          inside the timed region
+  roofline  dominant kernel = fwd_dense_kernel: algorithmic forward bytes (SURVEY.md §8d formula with
+          the realised N_k / N_i) / its CUDA-event duration, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference
+          the reference-style pure-PyTorch CPU path (oracle/torch_cpu_path.py: eager-torch rank
+          precompute + index_add_ scatter + autograd backward) on the box's host cores
+
+Multi-GPU (torchrun, one rank per GPU): samples are batch-sharded, B per rank (weak scaling), no
+collective on the data path; the NCCL all_gather of the voxel outputs named by BASELINE.json is timed
+separately and reported under "gather".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KERNELS_PER_STEP = 4 + 1 + 5 + 2     # rank_prepare, forward, bwd plan, backward (memsets not counted)
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(B, N, D, H, W, C, V, n_kept, n_iv):
+    """fp32 = int32 = 4 bytes."""
+    P, rows = B * N * D * H * W, B * N * H * W
+    fwd = 4 * (P + rows * C + 3 * n_kept + 2 * n_iv + B * V * C)
+    bwd = 4 * (n_iv * C + 2 * P + 2 * rows * C + 3 * n_kept + 2 * rows)
+    pre = 4 * (3 * P + 3 * n_kept + 2 * n_iv)
+    return dict(fwd=fwd, bwd=bwd, pre=pre, total=fwd + bwd + pre)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:  # noqa: BLE001
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_inputs(shape, B, first_sample, device):
+    """coor (from the product's own get_lidar_coor on `device`), depth, feat (NHWC fp32), out_grad."""
+    import torch
+    from fusionocc_b200 import LSSViewTransformer
+    from fusionocc_b200.rig import make_calibration
+    vt = LSSViewTransformer(shape.grid_cfg(), shape.input_size, shape.downsample, in_channels=8,
+                            out_channels=shape.channels, collapse_z=False)
+    total = first_sample + B
+    cal = [c[first_sample:total].to(device) for c in make_calibration(shape, total)]
+    coor = vt.get_lidar_coor(*cal).contiguous()
+    N, D, C = shape.n_cams, vt.D, shape.channels
+    H, W = shape.feat_hw
+    X, Y, Z = vt._grid_xyz()
+    depth = torch.empty(B, N, D, H, W)
+    feat = torch.empty(B, N, H, W, C)
+    og = torch.empty(B, C, Z, Y, X)
+    for i in range(B):
+        b = first_sample + i
+        depth[i] = torch.randn(N, D, H, W, generator=torch.Generator().manual_seed(0 + 7919 * b)).softmax(dim=1)
+        feat[i] = torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(1 + 7919 * b)).permute(0, 2, 3, 1)
+        og[i] = torch.randn(C, Z, Y, X, generator=torch.Generator().manual_seed(2 + 7919 * b))
+    return vt, coor, depth, feat, og
+
+
+class NativeStep:
+    """Static device buffers + the four C-ABI calls of one step (what a C++ host would do)."""
+
+    def __init__(self, vt, coor, depth, feat, og):
+        import torch
+        from fusionocc_b200 import _cabi
+        self.torch, self.cabi, self.lib = torch, _cabi, _cabi.load()
+        lib = self.lib
+        dev = coor.device
+        self.dev = dev
+        self.B, self.N, self.D, self.H, self.W, _ = coor.shape
+        self.C = feat.shape[-1]
+        self.X, self.Y, self.Z = vt._grid_xyz()
+        self.V = self.X * self.Y * self.Z
+        self.P = self.B * self.N * self.D * self.H * self.W
+        self.rows = self.B * self.N * self.H * self.W
+        NV = self.B * self.V
+        self.cap_iv = min(self.P, NV)
+        self.lb = _cabi.f3(vt.grid_lower_bound.tolist())
+        self.itv = _cabi.f3(vt.grid_interval.tolist())
+        i32 = dict(dtype=torch.int32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.coor, self.depth, self.feat, self.og = coor, depth.to(dev), feat.to(dev).contiguous(), og.to(dev)
+        self.rb, self.rd, self.rf = (torch.empty(self.P, **i32) for _ in range(3))
+        self.st, self.ln = (torch.empty(self.cap_iv, **i32) for _ in range(2))
+        self.counts = torch.zeros(4, **i32)
+        self.fwd_plan = torch.empty(lib.fo_fwd_plan_bytes(NV, self.P), **u8)
+        self.rank_scratch = torch.empty(lib.fo_rank_prepare_scratch_bytes(self.P, NV), **u8)
+        self.bwd_plan = torch.empty(lib.fo_bwd_plan_bytes(self.P, self.rows), **u8)
+        self.bwd_scratch = torch.empty(lib.fo_bwd_scratch_bytes(self.cap_iv, self.C, 0), **u8)
+        self.out = torch.empty(self.B, self.C, self.Z, self.Y, self.X, device=dev)
+        self.dg = torch.empty_like(self.depth)
+        self.fg = torch.empty_like(self.feat)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _s(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def rank_prepare(self):
+        p, L = self._p, self.lib
+        self.cabi.check(L.fo_rank_prepare(self._s(), p(self.coor), self.B, self.N, self.D, self.H, self.W, self.lb,
+                                          self.itv, self.X, self.Y, self.Z, p(self.rb), p(self.rd), p(self.rf),
+                                          p(self.st), p(self.ln), p(self.counts), p(self.fwd_plan),
+                                          self.fwd_plan.numel(), p(self.rank_scratch), self.rank_scratch.numel()),
+                        'fo_rank_prepare')
+
+    def forward(self):
+        p, L = self._p, self.lib
+        self.cabi.check(L.fo_bev_pool_v2_forward(
+            self._s(), self.C, p(self.depth), p(self.feat), p(self.rd), p(self.rf), p(self.rb), p(self.st),
+            p(self.ln), self.P, self.cap_iv, ctypes.c_void_p(self.counts.data_ptr() + 4), self.B, self.V,
+            p(self.out), 0, 1, p(self.fwd_plan), self.fwd_plan.numel()), 'fo_bev_pool_v2_forward')
+
+    def bwd_plan_build(self):
+        p, L = self._p, self.lib
+        self.cabi.check(L.fo_bwd_plan_build(self._s(), p(self.rf), self.P, p(self.counts), self.rows,
+                                            p(self.bwd_plan), self.bwd_plan.numel()), 'fo_bwd_plan_build')
+
+    def backward(self):
+        p, L = self._p, self.lib
+        self.cabi.check(L.fo_bev_pool_v2_backward(
+            self._s(), self.C, p(self.og), 0, p(self.depth), p(self.feat), p(self.rd), p(self.rf), p(self.rb),
+            p(self.st), p(self.ln), self.P, self.cap_iv, p(self.counts), self.B, self.V, self.P, self.rows,
+            p(self.dg), p(self.fg), p(self.fwd_plan), self.fwd_plan.numel(), p(self.bwd_plan),
+            self.bwd_plan.numel(), p(self.bwd_scratch), self.bwd_scratch.numel()), 'fo_bev_pool_v2_backward')
+
+    def step(self, events=None):
+        if events is None:
+            self.rank_prepare(); self.forward(); self.bwd_plan_build(); self.backward()
+            return
+        s = self.torch.cuda.current_stream(self.dev)
+        events[0].record(s); self.rank_prepare()
+        events[1].record(s); self.forward()
+        events[2].record(s); self.bwd_plan_build()
+        events[3].record(s); self.backward()
+        events[4].record(s)
+
+
+class HostStep:
+    """e2e: pinned host buffers -> fo_view_transform_host -> pinned host buffers, batch split in
+    chunks over streams so H2D, kernels and D2H of different chunks overlap."""
+
+    def __init__(self, ns: NativeStep, n_chunks: int):
+        import torch
+        self.torch, self.ns = torch, ns
+        lib = ns.lib
+        B = ns.B
+        n_chunks = max(1, min(n_chunks, B))
+        while B % n_chunks:
+            n_chunks -= 1
+        self.n_chunks, self.cb = n_chunks, B // n_chunks
+        pin = lambda x: x.detach().cpu().contiguous().pin_memory()
+        self.h_coor, self.h_depth, self.h_feat, self.h_og = pin(ns.coor), pin(ns.depth), pin(ns.feat), pin(ns.og)
+        self.h_out = torch.empty(ns.out.shape).pin_memory()
+        self.h_dg = torch.empty(ns.depth.shape).pin_memory()
+        self.h_fg = torch.empty(ns.feat.shape).pin_memory()
+        self.h_counts = torch.zeros(n_chunks, 4, dtype=torch.int32).pin_memory()
+        wsb = lib.fo_view_transform_host_workspace_bytes(self.cb, ns.N, ns.D, ns.H, ns.W, ns.C, ns.X, ns.Y, ns.Z, 1)
+        self.ws = [torch.empty(wsb, dtype=torch.uint8, device=ns.dev) for _ in range(n_chunks)]
+        self.streams = [torch.cuda.Stream(device=ns.dev) for _ in range(n_chunks)]
+        el = lambda t: t.numel() * t.element_size()
+        self.h2d_bytes = el(self.h_coor) + el(self.h_depth) + el(self.h_feat) + el(self.h_og)
+        self.d2h_bytes = el(self.h_out) + el(self.h_dg) + el(self.h_fg) + 16 * n_chunks
+
+    def step(self):
+        ns, p = self.ns, NativeStep._p
+        cur = self.torch.cuda.current_stream(ns.dev)
+        for i, s in enumerate(self.streams):
+            s.wait_stream(cur)
+            sl = slice(i * self.cb, (i + 1) * self.cb)
+            rc = ns.lib.fo_view_transform_host(
+                ctypes.c_void_p(s.cuda_stream), p(self.h_coor[sl]), p(self.h_depth[sl]), p(self.h_feat[sl]),
+                p(self.h_og[sl]), self.cb, ns.N, ns.D, ns.H, ns.W, ns.C, ns.lb, ns.itv, ns.X, ns.Y, ns.Z,
+                p(self.h_out[sl]), p(self.h_dg[sl]), p(self.h_fg[sl]), p(self.h_counts[i]), p(self.ws[i]),
+                self.ws[i].numel())
+            ns.cabi.check(rc, 'fo_view_transform_host')
+        for s in self.streams:
+            cur.wait_stream(s)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(shape, steps, warmup, budget_s=None):
+    """The reference-style CPU path on host cores, one sample per step (bounded sample of the batch)."""
+    import torch
+    from fusionocc_b200.rig import make_calibration, make_out_grad, make_values
+    from oracle import rank_oracle as ro
+    from oracle.torch_cpu_path import bev_pool_v2_pure_torch, voxel_pooling_prepare_v2_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lb, itv, gs = (torch.from_numpy(a) for a in ro.create_grid_infos(**shape.grid_cfg()))
+    fr = ro.create_frustum(shape.depth_cfg, shape.input_size, shape.downsample)
+    cal = make_calibration(shape, 1)
+    coor = ro.get_lidar_coor(fr, *cal)
+    depth, feat_nchw = make_values(shape, 1)
+    X, Y, Z = int(gs[0]), int(gs[1]), int(gs[2])
+    og = make_out_grad(1, shape.channels, Z, Y, X)
+    bshape = (1, Z, Y, X, shape.channels)
+
+    def one():
+        rb, rd, rf, st, ln = voxel_pooling_prepare_v2_torch(coor, lb, itv, gs)
+        d = depth.detach().requires_grad_(True)
+        f = feat_nchw.detach().requires_grad_(True)
+        out = bev_pool_v2_pure_torch(d, f.permute(0, 1, 3, 4, 2), rd, rf, rb, bshape)
+        out.backward(og)
+        return out
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, dt / done * 1e3, done, cores
+
+
+def run_reference(args):
+    from fusionocc_b200.rig import SHAPES
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    shape = SHAPES[args.shape]
+    sps, ms, done, cores = cpu_reference_run(shape, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'voxel-pool samples/s (rank precompute + bev_pool_v2 fwd + bwd)',
+        'value': sps, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': workload_config(shape, args.batch, 'gpu'),
+        'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': '1 sample per step (1/8 of the GPU arm\'s per-GPU batch), same shape, '
+                                   'eager-torch rank precompute + index_add_ scatter + autograd backward '
+                                   '(oracle/torch_cpu_path.py)'},
+        'e2e': {'value': sps, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(shape, B, where):
+    H, W = shape.feat_hw
+    return {'workload': f'FusionOcc view transform: rank precompute + bev_pool_v2 fwd + bwd, {shape.n_cams} cams '
+                        f'{shape.input_size[0]}x{shape.input_size[1]} ({H}x{W} feat), D={shape.D}, C={shape.channels}, '
+                        f'grid 200x200x16, batch {B} per {"GPU" if where == "gpu" else "step"}',
+            'shape': shape.name, 'batch_per_gpu': B, 'n_cams': shape.n_cams, 'D': shape.D, 'C': shape.channels,
+            'feat_hw': [H, W], 'grid_zyx': [16, 200, 200],
+            'l2_policy': 'working set >> L2: the dense voxel output alone is 81.92 MB x batch per step '
+                         '(655 MB at batch 8) vs 126 MB L2; no explicit flush' if where == 'gpu' else 'n/a'}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fusionocc_b200.rig import SHAPES
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (impl=ours) needs a CUDA device: the product has no CPU path')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    shape = SHAPES[args.shape]
+    B = args.batch
+    vt, coor, depth, feat, og = make_inputs(shape, B, rank * B, dev)
+    ns = NativeStep(vt, coor, depth, feat, og)
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        ns.step()
+    torch.cuda.synchronize()
+    n_kept, n_iv = (int(v) for v in ns.counts[:2].tolist())
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(K):
+        ns.step(ev[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    phase = [sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(K)) / K for i in range(4)]
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / K
+    value = world * B * K / (total_ms * 1e-3)
+
+    # ---- e2e through the host-buffer entry
+    hs = HostStep(ns, n_chunks=args.e2e_chunks)
+    for _ in range(2):
+        hs.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Ke = max(3, min(K, args.e2e_steps))
+    e0.record()
+    for _ in range(Ke):
+        hs.step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = world * B * Ke / (e2e_ms * 1e-3)
+
+    # ---- NCCL gather of the voxel outputs (BASELINE.json: "NCCL used only to gather outputs"), separate
+    gather = None
+    if world > 1:
+        gbuf = torch.empty((world,) + tuple(ns.out.shape), device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(gbuf, ns.out)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(gbuf, ns.out)
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1) / 5
+        tt = torch.tensor([gms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        gms = float(tt.item())
+        recv = (world - 1) * ns.out.numel() * 4
+        gather = {'collective': 'all_gather_into_tensor (NCCL)', 'ms': gms, 'recv_GBps_per_rank': recv / gms / 1e6,
+                  'bytes_per_rank': ns.out.numel() * 4, 'note': 'timed separately; not part of value'}
+        del gbuf
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    ab = algorithmic_bytes(B, ns.N, ns.D, ns.H, ns.W, ns.C, ns.V, n_kept, n_iv)
+    peak, peak_src = measured_peak()
+    fwd_ms = phase[1]
+    achieved = ab['fwd'] / (fwd_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic_fwd_dense.json')
+    if os.path.isfile(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(f'{shape.name}_B{B}')
+        except Exception:  # noqa: BLE001
+            traffic = None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, done, cores = cpu_reference_run(shape, 200, 1, budget_s=args.cpu_budget)
+        cpu = {'value': sps, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{done} single-sample steps of the same shape (~{args.cpu_budget:.0f} s of CPU work): '
+                         'eager-torch rank precompute + index_add_ scatter + autograd backward',
+               'ms_per_sample': ms}
+
+    line = {
+        'metric': 'voxel-pool samples/s (rank precompute + bev_pool_v2 fwd + bwd)',
+        'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(shape, B, 'gpu'),
+        'realised': {'n_points': ns.P, 'n_kept': n_kept, 'n_intervals': n_iv},
+        'phases_ms': {'rank_prepare': phase[0], 'forward': phase[1], 'bwd_plan': phase[2], 'backward': phase[3]},
+        'algorithmic_MB_per_step': {k: v / 1e6 for k, v in ab.items()},
+        'step_hbm_frac': ab['total'] / (ms_per_step * 1e-3) / 1e9 / peak,
+        'roofline': {'kernel': 'fwd_dense_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': ab['fwd'], 'launch_ms': fwd_ms},
+        'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': hs.h2d_bytes,
+                'd2h_bytes_per_step': hs.d2h_bytes, 'ms_per_step': e2e_ms / Ke, 'steps': Ke,
+                'chunks': hs.n_chunks, 'api': 'fo_view_transform_host (C ABI, pinned host buffers)'},
+        'gpu_launches': KERNELS_PER_STEP * K,
+        'clocks': clocks,
+    }
+    if cpu:
+        line['cpu_baseline'] = cpu
+    if gather:
+        line['gather'] = gather
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--shape', default='base', choices=['base', 'native', 'stress'])
+    ap.add_argument('--batch', type=int, default=8, help='samples per GPU per step')
+    ap.add_argument('--e2e-steps', type=int, default=10)
+    ap.add_argument('--e2e-chunks', type=int, default=4)
+    ap.add_argument('--cpu-budget', type=float, default=15.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -69,6 +69,7 @@ class VoxelPoolPlan:
         self.B, self.n_vox = B, n_vox
         self.n_points, self.n_intervals = n_points, n_intervals     # capacities when counts_dev is set
         self.counts_dev = counts_dev        # int32[4] {n_kept, n_intervals, 0, 0} or None
+        self.trusted = False                # True: produced by fo_rank_prepare (always sorted, in range)
 
     def n_intervals_dev_ptr(self):
         if self.counts_dev is None:
@@ -154,7 +155,8 @@ def native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_sta
         _cabi.check(lib.fo_bev_pool_v2_forward(
             _stream(dev), C, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat), _p(ranks_bev),
             _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals, plan.n_intervals_dev_ptr(),
-            B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward')
+            B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, _cabi.FO_FWD_ASSUME_SORTED if plan.trusted else 0,
+            _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward')
     return out
 
 

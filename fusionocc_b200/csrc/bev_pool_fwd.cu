@@ -232,7 +232,7 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
                                       const int32_t *ranks_bev, const int32_t *interval_starts,
                                       const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
                                       const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, float *out,
-                                      int32_t out_layout, const void *plan, size_t plan_bytes) {
+                                      int32_t out_layout, int32_t flags, const void *plan, size_t plan_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FO_CHECK_ARG(c >= 1, "channels must be positive (got %d)", c);
     FO_CHECK_ARG(B >= 1 && n_vox >= 1, "B and voxels per sample must be positive");
@@ -266,6 +266,7 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     // order-agnostic path, guarded by the plan's flag on the device (no host sync); unconditional when
     // the staged tile does not fit shared memory.
     const int need_flag = dense_ok ? 1 : 0;
+    if (dense_ok && (flags & FO_FWD_ASSUME_SORTED)) return FO_OK;
     const int64_t total = (int64_t)B * n_vox * c;
     const int64_t n4 = total / 4;
     const int n_tail = (int)(total - n4 * 4);

@@ -236,20 +236,19 @@ __device__ inline void warp_sort_segment(int32_t *seg, int len, int *smem /* kSo
         __syncwarp();
         return;
     }
-    // very long segment (degenerate geometry): bitonic network directly in global memory, padded
-    // virtually with +inf beyond len.  Compare-exchange pairs are disjoint within a (k, j) stage.
+    // very long segment (degenerate geometry): sorting network directly in global memory.  This is the
+    // "always ascending" bitonic form — the first stage of every merge pairs i with its mirror
+    // i ^ (k-1), later stages with i ^ j — so every compare-exchange moves the minimum to the lower
+    // index and the virtual +inf padding beyond `len` never has to move: no out-of-range access.
+    // Compare-exchange pairs are disjoint within a stage.
     for (long long k = 2; k <= n2; k <<= 1) {
         for (long long j = k >> 1; j > 0; j >>= 1) {
-            for (long long i = lane; i < n2; i += 32) {
-                const long long l = i ^ j;
-                if (l > i) {
-                    const int a = (i < len) ? seg[i] : INT_MAX;
-                    const int b = (l < len) ? seg[l] : INT_MAX;
-                    const bool up = ((i & k) == 0);
-                    if ((a > b) == up) {
-                        if (i < len) seg[i] = b;
-                        if (l < len) seg[l] = a;
-                    }
+            const long long x = (j == (k >> 1)) ? (k - 1) : j;
+            for (long long i = lane; i < len; i += 32) {
+                const long long l = i ^ x;
+                if (l > i && l < len) {
+                    const int a = seg[i], b = seg[l];
+                    if (a > b) { seg[i] = b; seg[l] = a; }
                 }
             }
             __threadfence_block();

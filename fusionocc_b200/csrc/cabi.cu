@@ -115,7 +115,8 @@ extern "C" int fo_view_transform_host(fo_stream_t stream_, const float *coor_hos
                                  w.rank_scratch_bytes))
         return rc;
     if (int rc = fo_bev_pool_v2_forward(stream_, c, w.depth, w.feat, w.rd, w.rf, w.rb, w.st, w.ln, P, cap_iv,
-                                        w.counts + 1, B, V, w.out, FO_LAYOUT_BCZYX, w.fwd_plan, w.fwd_plan_bytes))
+                                        w.counts + 1, B, V, w.out, FO_LAYOUT_BCZYX, FO_FWD_ASSUME_SORTED, w.fwd_plan,
+                                        w.fwd_plan_bytes))
         return rc;
     FO_CUDA(cudaMemcpyAsync(out_host, w.out, (size_t)NV * c * 4, cudaMemcpyDeviceToHost, stream));
     if (bwd) {

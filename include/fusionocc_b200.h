@@ -49,6 +49,10 @@ extern "C" {
 #define FO_ERR_UNSUPPORTED     3   /* shape outside what the kernels implement                  */
 #define FO_ERR_SCRATCH         4   /* scratch / plan buffer smaller than fo_*_bytes() asked for */
 
+/* fo_bev_pool_v2_forward flags */
+#define FO_FWD_ASSUME_SORTED 1   /* plan is known clean (built by fo_rank_prepare, or its flags were read back
+                                    as 0): skip launching the two device-guarded order-agnostic kernels */
+
 /* Memory layout of the dense voxel tensor (the forward output / the backward's out_grad). */
 #define FO_LAYOUT_BCZYX  0   /* contiguous (B,C,Z,Y,X): what bev_pool_v2() returns (bev_pool.py:91)      */
 #define FO_LAYOUT_BZYXC  1   /* contiguous (B,Z,Y,X,C): what the reference extension itself writes/reads */
@@ -92,7 +96,9 @@ int fo_fwd_plan_build(fo_stream_t stream,
  *   out          fp32 B*c*n_voxels_per_sample elements, layout `out_layout`
  *   plan         from fo_fwd_plan_build for the same index arrays
  * Interval voxels that are not strictly increasing, or ranks outside the grid, are detected by the
- * plan; the call then takes the order-agnostic scatter path (same results for valid input).
+ * plan; the call then takes the order-agnostic scatter path (same results for valid input).  The
+ * choice is made ON THE DEVICE from the plan's flag word (no host sync): both paths are enqueued and
+ * the wrong one exits at once, unless FO_FWD_ASSUME_SORTED is passed.
  * ------------------------------------------------------------------------------------------------ */
 int fo_bev_pool_v2_forward(fo_stream_t stream, int32_t c,
                            const float *depth, const float *feat,
@@ -101,7 +107,7 @@ int fo_bev_pool_v2_forward(fo_stream_t stream, int32_t c,
                            const int32_t *interval_starts, const int32_t *interval_lengths,
                            int64_t n_points, int64_t n_intervals, const int32_t *n_intervals_dev,
                            int32_t B, int64_t n_voxels_per_sample,
-                           float *out, int32_t out_layout,
+                           float *out, int32_t out_layout, int32_t flags,
                            const void *plan, size_t plan_bytes);
 
 /* ------------------------------------------------------------------------------------------------
@@ -152,7 +158,7 @@ int fo_bev_pool_v2_backward(fo_stream_t stream, int32_t c,
  * Outputs (capacity n_points_total each for ranks_*, min(n_points_total, B*Z*Y*X) for intervals):
  *   ranks_bev / ranks_depth / ranks_feat / interval_starts / interval_lengths  int32
  *   counts_dev   int32[4] on device: {n_kept, n_intervals, 0, 0}
- *   fwd_plan     optional (may be NULL): filled as by fo_fwd_plan_build
+ *   fwd_plan     required: filled as by fo_fwd_plan_build (the scan produces the tile table for free)
  * Integer arithmetic is exact (the reference's fp32 rank arithmetic is exact only for
  * B*Z*Y*X < 2^24; above that the reference itself is wrong).
  * ------------------------------------------------------------------------------------------------ */

@@ -473,7 +473,7 @@ def test_invalid_arguments_raise():
     with pytest.raises(RuntimeError):
         bev_pool_v2(torch.zeros(1, 1, 2, 2, 2), z(1, 1, 2, 2, 4), zi(1), zi(1), zi(1), (1, 1, 2, 2, 4), zi(1), zi(1))
     lib = _cabi.load()
-    rc = lib.fo_bev_pool_v2_forward(None, 0, None, None, None, None, None, None, None, 0, 0, None, 1, 1, None, 0,
+    rc = lib.fo_bev_pool_v2_forward(None, 0, None, None, None, None, None, None, None, 0, 0, None, 1, 1, None, 0, 0,
                                     None, 0)
     assert rc == 1 and b'channels' in lib.fo_last_error()
 
