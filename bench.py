@@ -42,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 4 + 1 + 5 + 2     # rank_prepare, forward, bwd plan, backward (memsets not counted)
+KERNELS_PER_STEP = 4 + 1 + 1 + 2     # rank_prepare, forward, bwd plan (structured), backward (memsets not counted)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,15 +196,16 @@ class NativeStep:
 
     def bwd_plan_build(self):
         p, L = self._p, self.lib
-        self.cabi.check(L.fo_bwd_plan_build(self._s(), p(self.rf), self.P, p(self.counts), self.rows,
-                                            p(self.bwd_plan), self.bwd_plan.numel()), 'fo_bwd_plan_build')
+        self.cabi.check(L.fo_bwd_plan_build(self._s(), p(self.rd), p(self.rf), self.P, p(self.counts), self.P,
+                                            self.rows, self.H * self.W, 1, p(self.fwd_plan), self.fwd_plan.numel(),
+                                            self.B, self.V, p(self.bwd_plan), self.bwd_plan.numel()),
+                        'fo_bwd_plan_build')
 
     def backward(self):
         p, L = self._p, self.lib
         self.cabi.check(L.fo_bev_pool_v2_backward(
-            self._s(), self.C, p(self.og), 0, p(self.depth), p(self.feat), p(self.rd), p(self.rf), p(self.rb),
-            p(self.st), p(self.ln), self.P, self.cap_iv, p(self.counts), self.B, self.V, self.P, self.rows,
-            p(self.dg), p(self.fg), p(self.fwd_plan), self.fwd_plan.numel(), p(self.bwd_plan),
+            self._s(), self.C, p(self.og), 0, p(self.depth), p(self.feat), self.P, self.cap_iv, self.B, self.V,
+            self.P, self.rows, p(self.dg), p(self.fg), p(self.fwd_plan), self.fwd_plan.numel(), p(self.bwd_plan),
             self.bwd_plan.numel(), p(self.bwd_scratch), self.bwd_scratch.numel()), 'fo_bev_pool_v2_backward')
 
     def step(self, events=None):

@@ -17,6 +17,7 @@ FO_OK = 0
 FO_LAYOUT_BCZYX = 0
 FO_LAYOUT_BZYXC = 1
 FO_FWD_ASSUME_SORTED = 1
+FO_BWD_PLAN_STRUCTURED = 1
 ABI_VERSION = 1
 
 _ERR_NAMES = {1: 'FO_ERR_INVALID_ARG', 2: 'FO_ERR_CUDA', 3: 'FO_ERR_UNSUPPORTED', 4: 'FO_ERR_SCRATCH'}
@@ -35,12 +36,12 @@ SIGNATURES = {
                                        c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_void_p, c_int32,
                                        c_int32, c_void_p, c_size_t]),
     'fo_bwd_plan_bytes': (c_size_t, [c_int64, c_int64]),
-    'fo_bwd_plan_build': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t]),
+    'fo_bwd_plan_build': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                  c_void_p, c_size_t, c_int32, c_int64, c_void_p, c_size_t]),
     'fo_bwd_scratch_bytes': (c_size_t, [c_int64, c_int32, c_int32]),
-    'fo_bev_pool_v2_backward': (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64,
-                                        c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
-                                        c_void_p, c_size_t]),
+    'fo_bev_pool_v2_backward': (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64,
+                                        c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p, c_size_t, c_void_p, c_size_t]),
     'fo_rank_prepare_scratch_bytes': (c_size_t, [c_int64, c_int64]),
     'fo_rank_prepare': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, _f3, _f3, c_int32,
                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -63,13 +63,15 @@ class VoxelPoolPlan:
 
     def __init__(self, fwd: torch.Tensor, B: int, n_vox: int, n_points: int, n_intervals: int,
                  counts_dev: Optional[torch.Tensor] = None):
-        self.fwd = fwd                      # uint8 plan buffer
+        self.fwd = fwd                      # uint8 plan buffer (its size fixes the layout)
         self.bwd: Optional[torch.Tensor] = None
         self.bwd_rows = -1
         self.B, self.n_vox = B, n_vox
         self.n_points, self.n_intervals = n_points, n_intervals     # capacities when counts_dev is set
         self.counts_dev = counts_dev        # int32[4] {n_kept, n_intervals, 0, 0} or None
         self.trusted = False                # True: produced by fo_rank_prepare (always sorted, in range)
+        self.structured_hw = 0              # H*W when produced by fo_rank_prepare (point<->pixel structure)
+        self.n_depth = 0                    # B*N*D*H*W when structured
 
     def n_intervals_dev_ptr(self):
         if self.counts_dev is None:
@@ -83,16 +85,22 @@ class VoxelPoolPlan:
         """Debug/test helper (synchronises): bit0 = unsorted interval voxels, bit1 = out of range."""
         return int(self.fwd[:4].view(torch.int32).item())
 
-    def ensure_bwd(self, ranks_feat: torch.Tensor, n_feat_rows: int) -> torch.Tensor:
+    def ensure_bwd(self, ranks_depth: torch.Tensor, ranks_feat: torch.Tensor, n_depth: int,
+                   n_feat_rows: int) -> torch.Tensor:
         if self.bwd is None or self.bwd_rows != n_feat_rows:
             lib = _cabi.load()
             dev = ranks_feat.device
-            nbytes = lib.fo_bwd_plan_bytes(self.n_points, n_feat_rows)
+            structured = (self.structured_hw > 0 and self.n_depth == n_depth and n_feat_rows % self.structured_hw == 0
+                          and n_depth % n_feat_rows == 0 and n_depth // n_feat_rows <= 256)
+            cap = n_depth if structured else self.n_points
+            nbytes = lib.fo_bwd_plan_bytes(cap, n_feat_rows)
             buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
-                _cabi.check(lib.fo_bwd_plan_build(_stream(dev), _p(ranks_feat), self.n_points,
-                                                  self.n_points_dev_ptr(), n_feat_rows, _p(buf), nbytes),
-                            'fo_bwd_plan_build')
+                _cabi.check(lib.fo_bwd_plan_build(
+                    _stream(dev), _p(ranks_depth), _p(ranks_feat), self.n_points, self.n_points_dev_ptr(), n_depth,
+                    n_feat_rows, self.structured_hw if structured else 0,
+                    _cabi.FO_BWD_PLAN_STRUCTURED if structured else 0, _p(self.fwd), self.fwd.numel(), self.B,
+                    self.n_vox, _p(buf), nbytes), 'fo_bwd_plan_build')
             self.bwd, self.bwd_rows = buf, n_feat_rows
         return self.bwd
 
@@ -103,7 +111,7 @@ def build_plan(ranks_bev: torch.Tensor, interval_starts: torch.Tensor, interval_
     lib = _cabi.load()
     dev = _require_cuda(ranks_bev, interval_starts, interval_lengths)
     n_points, n_intervals = ranks_bev.numel(), interval_lengths.numel()
-    nbytes = lib.fo_fwd_plan_bytes(B * n_vox, n_points)
+    nbytes = lib.fo_fwd_plan_bytes(B * n_vox, max(n_points, n_intervals))
     buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _cabi.check(lib.fo_fwd_plan_build(_stream(dev), _p(ranks_bev), _p(interval_starts), _p(interval_lengths),
@@ -160,22 +168,21 @@ def native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_sta
     return out
 
 
-def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
-                    interval_lengths, bev_feat_shape, plan: VoxelPoolPlan) -> Tuple[torch.Tensor, torch.Tensor]:
+def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, bev_feat_shape,
+                    plan: VoxelPoolPlan) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _cabi.load()
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
     dev = depth.device
     n_feat_rows = feat.numel() // C
-    bwd = plan.ensure_bwd(ranks_feat, n_feat_rows)
+    bwd = plan.ensure_bwd(ranks_depth, ranks_feat, depth.numel(), n_feat_rows)
     depth_grad = torch.empty_like(depth)
     feat_grad = torch.empty_like(feat)
     sbytes = lib.fo_bwd_scratch_bytes(plan.n_intervals, C, og_layout)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _cabi.check(lib.fo_bev_pool_v2_backward(
-            _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat),
-            _p(ranks_bev), _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals,
-            _p(plan.counts_dev), B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad), _p(feat_grad),
+            _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), plan.n_points, plan.n_intervals,
+            B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad), _p(feat_grad),
             _p(plan.fwd), plan.fwd.numel(), _p(bwd), bwd.numel(), _p(scratch), sbytes), 'fo_bev_pool_v2_backward')
     return depth_grad, feat_grad
 
@@ -229,8 +236,8 @@ class QuickCumsumCuda(torch.autograd.Function):
     def backward(ctx, out_grad):
         ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts, interval_lengths = ctx.saved_tensors
         out_grad, layout = _classify_out_grad(out_grad)
-        depth_grad, feat_grad = native_backward(out_grad, layout, depth, feat, ranks_depth, ranks_feat, ranks_bev,
-                                                interval_starts, interval_lengths, ctx.bev_feat_shape, ctx.plan)
+        depth_grad, feat_grad = native_backward(out_grad, layout, depth, feat, ranks_depth, ranks_feat,
+                                                ctx.bev_feat_shape, ctx.plan)
         return depth_grad, feat_grad, None, None, None, None, None, None, None
 
 

@@ -32,43 +32,45 @@ struct FwdArgs {
     float *out;
     const FwdPlanHeader *hdr;
     const int32_t *tile_off;
+    const int32_t *iv_vox;          // voxel id of every interval (plan)
 };
 
-// Sequential FMA over one interval, float4 per lane.  Loads for four points are issued before the
-// four dependent FMA steps so that an interval of length L costs ~L/4 memory round trips.
+// Sequential FMA over one interval, float4 per lane.  Points are taken in batches of four: all index
+// loads of a batch are issued together, then all value loads, then the four dependent FMA steps in
+// interval order — so an interval of length L costs 2*ceil(L/4) memory round trips, and the common
+// L <= 4 case exactly two.
 template <int NCHUNK>
 __device__ __forceinline__ void reduce_interval(float4 (&acc)[NCHUNK], const FwdArgs &a, int s, int len, int gl,
                                                 int c4 /* C/4 */) {
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = 0;
-    for (; i + 4 <= len; i += 4) {
+    for (int i = 0; i < len; i += 4) {
         int p[4], q[4];
         float d[4];
         float4 f[4][NCHUNK];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { p[u] = __ldg(a.rd + s + i + u); q[u] = __ldg(a.rf + s + i + u); }
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = i + u < len;
+            p[u] = ok ? __ldg(a.rd + s + i + u) : -1;
+            q[u] = ok ? __ldg(a.rf + s + i + u) : 0;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            d[u] = __ldg(a.depth + p[u]);
+            const bool ok = p[u] >= 0;
+            d[u] = ok ? __ldg(a.depth + p[u]) : 0.f;
 #pragma unroll
             for (int ch = 0; ch < NCHUNK; ++ch) {
                 const int idx = gl + kGroupLanes * ch;
-                f[u][ch] = (idx < c4) ? ldg4(a.feat + ((int64_t)q[u] * c4 + idx) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                f[u][ch] = (ok && idx < c4) ? ldg4(a.feat + ((int64_t)q[u] * c4 + idx) * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+            if (i + u < len) {
 #pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) fma4(acc[ch], f[u][ch], d[u]);
-    }
-    for (; i < len; ++i) {
-        const int p = __ldg(a.rd + s + i), q = __ldg(a.rf + s + i);
-        const float d = __ldg(a.depth + p);
-#pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            const int idx = gl + kGroupLanes * ch;
-            if (idx < c4) fma4(acc[ch], ldg4(a.feat + ((int64_t)q * c4 + idx) * 4), d);
+                for (int ch = 0; ch < NCHUNK; ++ch) fma4(acc[ch], f[u][ch], d[u]);
+            }
         }
     }
 }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
             const int g = tid / kGroupLanes, gl = tid % kGroupLanes, c4 = C >> 2;
             for (int k = k0 + g; k < k1; k += kGroupsPerCta) {
                 const int s = __ldg(a.starts + k), len = __ldg(a.lengths + k);
-                const int vl = (int)(__ldg(a.rb + s) - vbase);
+                const int vl = (int)(__ldg(a.iv_vox + k) - vbase);
                 if ((unsigned)vl >= (unsigned)nv) continue;      // plan / arrays mismatch: never write outside the tile
                 float4 acc[NCHUNK];
                 reduce_interval<NCHUNK>(acc, a, s, len, gl, c4);
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
             // scalar path: one warp per interval, lanes stride over channels
             for (int k = k0 + warp; k < k1; k += kThreads / 32) {
                 const int s = __ldg(a.starts + k), len = __ldg(a.lengths + k);
-                const int vl = (int)(__ldg(a.rb + s) - vbase);
+                const int vl = (int)(__ldg(a.iv_vox + k) - vbase);
                 if ((unsigned)vl >= (unsigned)nv) continue;
                 for (int c = lane; c < C; c += 32) {
                     float psum = 0.f;
@@ -241,19 +243,14 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     FO_CHECK_ARG(n_points >= 0 && n_intervals >= 0 && n_points < INT_MAX, "negative or oversized counts");
     FO_CHECK_ARG(n_intervals == 0 || (depth && feat && ranks_depth && ranks_feat && ranks_bev && interval_starts &&
                                       interval_lengths), "NULL input array");
-    FO_CHECK_ARG(plan != nullptr, "plan is NULL (build it with fo_fwd_plan_build or fo_rank_prepare)");
-    FO_CHECK_ARG((int64_t)B * n_vox < INT_MAX, "B*Z*Y*X does not fit int32 ranks");
-    const int64_t tps = tiles_per_sample(n_vox);
-    const int64_t n_tiles = tps * B;
-    const size_t need = 256 + fwd_plan_tile_bytes(n_tiles);
-    if (plan_bytes < need) return set_error(FO_ERR_SCRATCH, "forward plan buffer is %zu bytes, need >= %zu", plan_bytes, need);
-    FwdPlanView pv = fwd_plan_view(const_cast<void *>(plan), n_tiles);
+    FwdPlanView pv; int64_t n_tiles; int tps;
+    if (int rc = open_fwd_plan_const(plan, plan_bytes, B, n_vox, n_points, &pv, &n_tiles, &tps)) return rc;
 
     FwdArgs a;
     a.depth = depth; a.feat = feat; a.rd = ranks_depth; a.rf = ranks_feat; a.rb = ranks_bev;
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = n_points; a.n_intervals = n_intervals; a.n_intervals_dev = n_intervals_dev;
-    a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.tile_off = pv.tile_off;
+    a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.tile_off = pv.tile_off; a.iv_vox = pv.iv_vox;
 
     const size_t smem = (size_t)kTile * (c + 1) * sizeof(float);
     const bool dense_ok = smem <= 200 * 1024;
@@ -272,11 +269,11 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     const int n_tail = (int)(total - n4 * 4);
     zero_if_flag_kernel<<<148 * 8, 256, 0, stream>>>((float4 *)out, n4, out + n4 * 4, n_tail, pv.hdr, need_flag);
     FO_LAUNCH_CHECK("zero_if_flag_kernel");
-    const int blocks = (int)((n_intervals * 32 + 255) / 256 > 148 * 8 ? 148 * 8 : (n_intervals * 32 + 255) / 256);
+    const int blocks = grid_for(n_intervals * 32, 256, 8);
     if (out_layout == FO_LAYOUT_BCZYX)
-        fwd_scatter_kernel<FO_LAYOUT_BCZYX><<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(a, need_flag);
+        fwd_scatter_kernel<FO_LAYOUT_BCZYX><<<blocks, 256, 0, stream>>>(a, need_flag);
     else
-        fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(a, need_flag);
+        fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<blocks, 256, 0, stream>>>(a, need_flag);
     FO_LAUNCH_CHECK("fwd_scatter_kernel");
     return FO_OK;
 }
@@ -291,7 +288,7 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.depth = depth; a.feat = feat; a.rd = ranks_depth; a.rf = ranks_feat; a.rb = ranks_bev;
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
-    a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.tile_off = nullptr;
+    a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.tile_off = nullptr; a.iv_vox = nullptr;
     int64_t blocks = ((int64_t)n_intervals * 32 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<(int)blocks, 256, 0, 0>>>(a, 0);

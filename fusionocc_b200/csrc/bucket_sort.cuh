@@ -261,14 +261,28 @@ struct OrderArgs {
     int32_t *sorted;            // in/out: per-bucket segments of original indices (becomes ranks_depth)
     const int32_t *iv_starts;
     const int32_t *iv_lengths;
-    const int32_t *iv_bucket;   // forward flavour only
+    const int32_t *iv_bucket;   // forward flavour only (= iv_vox of the plan)
     const int32_t *n_intervals; // device count
     // forward flavour outputs (nullptr for the backward plan)
     int32_t *ranks_feat;
     int32_t *ranks_bev;
     int32_t *pos2iv;
+    int32_t *pt2pos;            // frustum point -> sorted position (its -1 entries were written by voxelise)
     int32_t dhw, hw;            // D*H*W and H*W: ranks_feat = (p / dhw) * hw + p % hw  (view_transformer.py:239-244)
 };
+
+// 19-comparator optimal sorting network for 8 keys (ascending)
+__device__ __forceinline__ void sort8(int (&v)[8]) {
+    cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+    cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+    cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
+    cswap(v[1], v[5]); cswap(v[2], v[6]);
+    cswap(v[1], v[4]); cswap(v[3], v[6]);
+    cswap(v[2], v[4]); cswap(v[3], v[5]);
+    cswap(v[3], v[4]);
+}
+
+constexpr int kLaneSortMax = 8;   // intervals up to this length are ordered by one lane in registers
 
 template <bool kForward>
 __global__ void __launch_bounds__(kSortThreads) order_segments_kernel(OrderArgs a) {
@@ -283,26 +297,25 @@ __global__ void __launch_bounds__(kSortThreads) order_segments_kernel(OrderArgs 
             len = a.iv_lengths[k];
             if (kForward) bucket = a.iv_bucket[k];
         }
-        if (len > 0 && len <= 4) {
-            int v0 = a.sorted[s];
-            int v1 = len > 1 ? a.sorted[s + 1] : INT_MAX;
-            int v2 = len > 2 ? a.sorted[s + 2] : INT_MAX;
-            int v3 = len > 3 ? a.sorted[s + 3] : INT_MAX;
-            cswap(v0, v1); cswap(v2, v3); cswap(v0, v2); cswap(v1, v3); cswap(v1, v2);
-            const int v[4] = {v0, v1, v2, v3};
+        if (len > 0 && len <= kLaneSortMax) {
+            int v[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
+            if (len > 1) sort8(v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
                 if (j < len) {
                     if (len > 1) a.sorted[s + j] = v[j];
                     if (kForward) {
                         a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
                         a.ranks_bev[s + j] = bucket;
                         a.pos2iv[s + j] = k;
+                        a.pt2pos[v[j]] = s + j;
                     }
                 }
             }
         }
-        unsigned longmask = __ballot_sync(0xffffffffu, len > 4);
+        unsigned longmask = __ballot_sync(0xffffffffu, len > kLaneSortMax);
         while (longmask) {
             const int src = __ffs(longmask) - 1;
             longmask &= longmask - 1;
@@ -317,6 +330,7 @@ __global__ void __launch_bounds__(kSortThreads) order_segments_kernel(OrderArgs 
                     a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
                     a.ranks_bev[ls + j] = lb;
                     a.pos2iv[ls + j] = base + src;
+                    a.pt2pos[p] = ls + j;
                 }
             }
         }

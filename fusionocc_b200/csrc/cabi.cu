@@ -120,11 +120,12 @@ extern "C" int fo_view_transform_host(fo_stream_t stream_, const float *coor_hos
         return rc;
     FO_CUDA(cudaMemcpyAsync(out_host, w.out, (size_t)NV * c * 4, cudaMemcpyDeviceToHost, stream));
     if (bwd) {
-        if (int rc = fo_bwd_plan_build(stream_, w.rf, P, w.counts, rows, w.bwd_plan, w.bwd_plan_bytes)) return rc;
-        if (int rc = fo_bev_pool_v2_backward(stream_, c, w.og, FO_LAYOUT_BCZYX, w.depth, w.feat, w.rd, w.rf, w.rb, w.st,
-                                             w.ln, P, cap_iv, w.counts, B, V, P, rows, w.dg, w.fg, w.fwd_plan,
-                                             w.fwd_plan_bytes, w.bwd_plan, w.bwd_plan_bytes, w.bwd_scratch,
-                                             w.bwd_scratch_bytes))
+        if (int rc = fo_bwd_plan_build(stream_, w.rd, w.rf, P, w.counts, P, rows, H * W, FO_BWD_PLAN_STRUCTURED,
+                                       w.fwd_plan, w.fwd_plan_bytes, B, V, w.bwd_plan, w.bwd_plan_bytes))
+            return rc;
+        if (int rc = fo_bev_pool_v2_backward(stream_, c, w.og, FO_LAYOUT_BCZYX, w.depth, w.feat, P, cap_iv, B, V, P,
+                                             rows, w.dg, w.fg, w.fwd_plan, w.fwd_plan_bytes, w.bwd_plan,
+                                             w.bwd_plan_bytes, w.bwd_scratch, w.bwd_scratch_bytes))
             return rc;
         FO_CUDA(cudaMemcpyAsync(depth_grad_host, w.dg, (size_t)P * 4, cudaMemcpyDeviceToHost, stream));
         FO_CUDA(cudaMemcpyAsync(feat_grad_host, w.fg, (size_t)rows * c * 4, cudaMemcpyDeviceToHost, stream));

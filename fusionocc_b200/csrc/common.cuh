@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -15,11 +16,17 @@ namespace fo {
 
 // ----------------------------------------------------------------------------------------------
 // Tiling constants shared by the forward plan, the forward kernel and the backward gather.
-// A tile is FO_TILE_VOXELS consecutive voxels of ONE sample in flattened (z,y,x) order; in the
-// (B,C,Z,Y,X) output that is C contiguous runs of FO_TILE_VOXELS floats (512 B each).
+// A tile is kTile consecutive voxels of ONE sample in flattened (z,y,x) order; in the (B,C,Z,Y,X)
+// output that is C contiguous runs of kTile floats (512 B each).
+//
+// Sizing rule (measured, profiles/r01): a tile's critical path is 3-4 dependent L2/HBM round trips
+// (plan -> interval records -> point records -> values), ~2-3 us under load, while one SM's share of
+// HBM write bandwidth drains a 16 KB tile in ~0.37 us.  So >= 8 tiles must be in flight per SM:
+// 128-thread CTAs (4 warps, 16 interval groups) let 12 CTAs co-reside (17 KB smem, <= 64 regs).
 // ----------------------------------------------------------------------------------------------
 constexpr int kTile         = 128;   // voxels per tile
-constexpr int kThreads      = 256;   // threads per CTA of the tile kernels
+constexpr int kTileShift    = 7;
+constexpr int kThreads      = 128;   // threads per CTA of the tile kernels
 constexpr int kGroupLanes   = 8;     // lanes cooperating on one interval: 8 x float4 = 32 channels/pass
 constexpr int kGroupsPerCta = kThreads / kGroupLanes;
 constexpr int kMaxChunks    = 4;     // channels <= 8 lanes * 4 floats * 4 chunks = 128 on the vector path
@@ -33,52 +40,111 @@ struct __align__(16) FwdPlanHeader {
     int32_t n_tiles;
     int32_t tiles_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
-    int32_t reserved[12];
+    int32_t structured;      // 1: pt2pos is valid (plan produced by fo_rank_prepare)
+    int32_t reserved[11];
 };
 static_assert(sizeof(FwdPlanHeader) == 64, "header is one 64-byte block");
 
 struct __align__(16) BwdPlanHeader {
-    int32_t n_bwd_intervals; // live count of distinct ranks_feat values (written by the scan)
+    int32_t n_bwd_intervals; // live count of backward intervals (distinct ranks_feat values / pixels)
     int32_t n_points;        // live point count
-    int32_t reserved[14];
+    int32_t totals[2];       // scratch for the scan's totals
+    int32_t reserved[12];
 };
 static_assert(sizeof(BwdPlanHeader) == 64, "header is one 64-byte block");
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline int64_t tiles_per_sample(int64_t n_vox) { return (n_vox + kTile - 1) / kTile; }
 
-// Layout of the forward plan buffer:  [header | tile_off[n_tiles+1] | pos2iv[n_points_capacity]]
+// ----------------------------------------------------------------------------------------------
+// Forward plan buffer:
+//   [header(256) | tile_off[tiles bound + 1] | pos2iv[P_cap] | pt2pos[P_cap] | iv_vox[IV_cap]]
+//   tile_off[t]   first interval whose voxel lies in tile t (tile_off[n_tiles] = n_intervals)
+//   pos2iv[i]     interval id of sorted position i (rows of the backward's gathered out_grad)
+//   iv_vox[k]     voxel id (= ranks_bev) of interval k: saves the ranks_bev[starts[k]] round trip
+//   pt2pos[p]     sorted position of frustum point p, -1 if filtered (only when hdr.structured)
+//   P_cap = point capacity rounded up to 64, IV_cap = min(P_cap, B*Z*Y*X rounded up to 64).
+// ----------------------------------------------------------------------------------------------
 struct FwdPlanView {
     FwdPlanHeader *hdr;
     int32_t *tile_off;
     int32_t *pos2iv;
+    int32_t *iv_vox;
+    int32_t *pt2pos;
+    int64_t p_cap;           // point capacity of this buffer (multiple of 64)
+    int64_t iv_cap;          // interval capacity
 };
-__host__ __device__ inline int64_t tiles_per_sample(int64_t n_vox) { return (n_vox + kTile - 1) / kTile; }
-__host__ __device__ inline size_t fwd_plan_tile_bytes(int64_t n_tiles) {
-    return (size_t)align_up((n_tiles + 1) * 4, 256);
+__host__ inline int64_t fwd_plan_tiles_bound(int64_t n_vox_total) { return n_vox_total / kTile + 4096 + 1; }
+__host__ inline size_t fwd_plan_tile_bytes(int64_t n_vox_total) {
+    return (size_t)align_up((fwd_plan_tiles_bound(n_vox_total) + 1) * 4, 256);
 }
-inline FwdPlanView fwd_plan_view(void *plan, int64_t n_tiles) {
+__host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
+    const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
+    return 256 + fwd_plan_tile_bytes(n_vox_total) + (size_t)(8 * pc + 4 * (pc < nv ? pc : nv));
+}
+// The layout is a pure function of (n_vox_total, plan_bytes): every entry point is handed the same
+// plan_bytes the buffer was sized with and recovers the same pointers without reading the device.
+__host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_bytes, FwdPlanView *v) {
+    const size_t fixed = 256 + fwd_plan_tile_bytes(n_vox_total);
+    if (plan_bytes < fixed + 64 * 12) return false;
+    const int64_t rest = (int64_t)(plan_bytes - fixed), nv = align_up(n_vox_total, 64);
+    int64_t pc = rest / 12;
+    if (pc > nv) pc = (rest - 4 * nv) / 8;
+    pc = pc / 64 * 64;
     char *p = (char *)plan;
-    FwdPlanView v;
-    v.hdr = (FwdPlanHeader *)p;
-    v.tile_off = (int32_t *)(p + sizeof(FwdPlanHeader) + 192);          // 256-byte aligned
-    v.pos2iv = (int32_t *)((char *)v.tile_off + fwd_plan_tile_bytes(n_tiles));
-    return v;
+    v->hdr = (FwdPlanHeader *)p;             p += 256;
+    v->tile_off = (int32_t *)p;              p += fwd_plan_tile_bytes(n_vox_total);
+    v->pos2iv = (int32_t *)p;                p += pc * 4;
+    v->pt2pos = (int32_t *)p;                p += pc * 4;
+    v->iv_vox = (int32_t *)p;
+    v->p_cap = pc;
+    v->iv_cap = pc < nv ? pc : nv;
+    return true;
 }
 
-// Layout of the backward plan buffer:
-//   [header | bwd_pos[n_points_cap] | bwd_starts[n_rows] | bwd_lengths[n_rows] | bucket scratch...]
+// ----------------------------------------------------------------------------------------------
+// Backward plan buffer (the inverse interval ordering):
+//   [header(256) | starts[rows] | lengths[rows] | ids[rows] | bucket counters (generic build) |
+//    ent_p[cap] | ent_iv[cap] | pos[cap] | slot[cap]]
+//   backward interval m (one image pixel) covers entries [starts[m], +lengths[m]); entry j names the
+//   point's depth index ent_p[j] and its forward interval ent_iv[j]; ids[m] is the feature row.
+//   Entries are in ascending forward position = the order bev_pool.py:47-49 produces.
+//   pos / slot / counters are scratch of the generic (sort-based) build.
+// ----------------------------------------------------------------------------------------------
 struct BwdPlanView {
     BwdPlanHeader *hdr;
-    int32_t *bwd_pos;
-    int32_t *bwd_starts;
-    int32_t *bwd_lengths;
-    int32_t *bucket_ids;    // ranks_feat value of each backward interval
-    int32_t *cnt;           // [n_rows]   counters -> exclusive offsets
-    int32_t *slot;          // [n_points] arrival slot of each position inside its bucket
-    uint64_t *scan_state;   // decoupled look-back descriptors
-    int32_t *scan_counter;
-    size_t   zero_begin, zero_bytes;   // region that must be zeroed before a build
+    int32_t *starts, *lengths, *ids;
+    char *counters;          // bucket-sort zero region (cnt | scan state | tile counter)
+    int32_t *ent_p, *ent_iv, *pos, *slot;
+    int64_t cap;
 };
+__host__ inline size_t bucket_zero_bytes(int64_t n_buckets) {
+    const int64_t n_scan_tiles = (n_buckets + 4095) / 4096;
+    return (size_t)(align_up(n_buckets * 4, 256) + align_up(n_scan_tiles * 8, 256) + 256);
+}
+__host__ inline size_t bwd_plan_fixed_bytes(int64_t rows) {
+    return 256 + 3 * (size_t)align_up(rows * 4, 256) + bucket_zero_bytes(rows);
+}
+__host__ inline size_t bwd_plan_bytes_for(int64_t cap, int64_t rows) {
+    return bwd_plan_fixed_bytes(rows) + 16 * (size_t)align_up(cap > 0 ? cap : 1, 64);
+}
+__host__ inline bool bwd_plan_view(void *plan, int64_t rows, size_t plan_bytes, BwdPlanView *v) {
+    const size_t fixed = bwd_plan_fixed_bytes(rows);
+    if (plan_bytes < fixed + 16 * 64) return false;
+    const int64_t cap = (int64_t)((plan_bytes - fixed) / 16) / 64 * 64;
+    char *p = (char *)plan;
+    v->hdr = (BwdPlanHeader *)p;  p += 256;
+    v->starts = (int32_t *)p;     p += align_up(rows * 4, 256);
+    v->lengths = (int32_t *)p;    p += align_up(rows * 4, 256);
+    v->ids = (int32_t *)p;        p += align_up(rows * 4, 256);
+    v->counters = p;              p += bucket_zero_bytes(rows);
+    v->ent_p = (int32_t *)p;      p += cap * 4;
+    v->ent_iv = (int32_t *)p;     p += cap * 4;
+    v->pos = (int32_t *)p;        p += cap * 4;
+    v->slot = (int32_t *)p;
+    v->cap = cap;
+    return true;
+}
 
 // ----------------------------------------------------------------------------------------------
 // Error plumbing (thread-local message, integer status) — cabi.cu owns the storage.
@@ -106,6 +172,17 @@ int set_error(int code, const char *fmt, ...);
                                    cudaGetErrorString(e__));                                   \
     } while (0)
 
+// opens + validates a forward plan buffer (defined in rank_prepare.cu)
+int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
+                        FwdPlanView *pv, int64_t *n_tiles, int *tps);
+
+inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
+    int64_t b = (work_items + per_block - 1) / per_block;
+    const int64_t cap = 148 * (int64_t)ctas_per_sm;      // B200: 148 SMs
+    if (b > cap) b = cap;
+    return b < 1 ? 1 : (int)b;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Small device helpers
 // ----------------------------------------------------------------------------------------------
@@ -119,9 +196,8 @@ __device__ __forceinline__ void fma4(float4 &acc, const float4 &a, float b) {
     acc.w = fmaf(a.w, b, acc.w);
 }
 
-// streaming (evict-first) 32-bit store: the dense voxel tensor is written once and not re-read here
+// streaming (evict-first) store: the dense voxel tensor is written once and not re-read here
 __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
 #endif
 
 }  // namespace fo

@@ -3,8 +3,6 @@
 // Replaces projects/FusionOcc/fusionocc/necks/view_transformer.py:223-281 (voxel_pooling_prepare_v2)
 // and the backward re-sort of mmdet3d/ops/bev_pool_v2/bev_pool.py:47-57.  See bucket_sort.cuh for
 // the sort itself.  Every kernel here is HBM/L2-bound integer work; nothing is reshaped into GEMMs.
-#include <limits.h>
-
 #include "bucket_sort.cuh"
 
 namespace fo {
@@ -23,9 +21,9 @@ struct VoxArgs {
     float lbx, lby, lbz, ivx, ivy, ivz;
     int32_t X, Y, Z;
     int32_t *cnt;                // [B*Z*Y*X] zero-initialised
-    int32_t *key;                // [n_points] voxel id or -1
+    int32_t *key;                // [n_points] voxel id or -1 (lives in the plan: becomes pt2pos)
     int32_t *slot;               // [n_points]
-    FwdPlanHeader *hdr;          // optional: static fields initialised by thread 0
+    FwdPlanHeader *hdr;          // static fields initialised by thread 0
     int32_t n_tiles, tiles_per_sample;
 };
 
@@ -39,10 +37,11 @@ __device__ __forceinline__ int voxel_key(float x, float y, float z, int64_t b, c
 
 __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid == 0 && a.hdr) {
+    if (gtid == 0) {
         a.hdr->flags = 0;
         a.hdr->n_tiles = a.n_tiles;
         a.hdr->tiles_per_sample = a.tiles_per_sample;
+        a.hdr->structured = 1;
     }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_quads = a.n_points >> 2;
@@ -74,10 +73,12 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
 // K1 (backward flavour): keys are given (ranks_feat of each forward position).
 __global__ void __launch_bounds__(256) count_keys_kernel(const int32_t *__restrict__ keys, int64_t n_cap,
                                                          const int32_t *__restrict__ n_dev, int64_t n_buckets,
-                                                         int32_t *cnt, int32_t *slot) {
+                                                         int32_t *cnt, int32_t *slot, BwdPlanHeader *hdr) {
     const int64_t n = n_dev ? min((int64_t)max(*n_dev, 0), n_cap) : n_cap;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid == 0) { hdr->n_bwd_intervals = 0; hdr->n_points = (int)n; }
+    for (int64_t i = gtid; i < n; i += stride) {
         const int k = keys[i];
         slot[i] = (k >= 0 && k < n_buckets) ? atomicAdd(cnt + k, 1) : -1;
     }
@@ -106,6 +107,7 @@ __global__ void init_fwd_header_kernel(FwdPlanHeader *hdr, int n_tiles, int tps,
         hdr->n_tiles = n_tiles;
         hdr->tiles_per_sample = tps;
         hdr->n_intervals = n_intervals;
+        hdr->structured = 0;
     }
 }
 
@@ -120,7 +122,8 @@ __device__ __forceinline__ int interval_voxel(const int32_t *rb, const int32_t *
 __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
     const int32_t *__restrict__ rb, const int32_t *__restrict__ starts, const int32_t *__restrict__ lengths,
     int64_t n_points, int64_t n_cap, const int32_t *__restrict__ n_dev, int64_t vox_per_sample,
-    int64_t n_vox_total, int tps, int n_tiles, FwdPlanHeader *hdr, int32_t *tile_off, int32_t *pos2iv) {
+    int64_t n_vox_total, int tps, int n_tiles, FwdPlanHeader *hdr, int32_t *tile_off, int32_t *pos2iv,
+    int32_t *iv_vox) {
     const int64_t n = n_dev ? min((int64_t)max(*n_dev, 0), n_cap) : n_cap;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
     for (int64_t k = gtid; k < n; k += stride) {
         const int v = interval_voxel(rb, starts, lengths, (int)k, n_points, n_vox_total);
         const int vp = k > 0 ? interval_voxel(rb, starts, lengths, (int)k - 1, n_points, n_vox_total) : -1;
+        iv_vox[k] = v;
         if (v < 0) {
             atomicOr(&hdr->flags, kFlagOutOfRange | kFlagUnsorted);
             continue;
@@ -150,6 +154,81 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward plan, structured build (plans produced by fo_rank_prepare).
+// One warp per image pixel q = (b*N+n)*HW + hw: its <= D candidate points are p = ((b*N+n)*D + d)*HW + hw;
+// pt2pos gives each one's forward position (or -1).  The pixel's entries, in ascending forward
+// position (= ascending (ranks_bev, p): the order of bev_pool.py:47-49), are found by rank-by-counting
+// in registers — no sort passes, no atomics, fixed-stride rows of D entries.
+// ------------------------------------------------------------------------------------------------
+template <int R>   // R = ceil(D / 32) registers per lane
+__global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t *__restrict__ pt2pos,
+                                                                  const int32_t *__restrict__ pos2iv, int D, int HW,
+                                                                  int n_rows, BwdPlanHeader *hdr, int32_t *ent_p,
+                                                                  int32_t *ent_iv, int32_t *starts, int32_t *lengths,
+                                                                  int32_t *ids, const int32_t *n_points_dev) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->n_bwd_intervals = n_rows;
+        hdr->n_points = n_points_dev ? *n_points_dev : 0;
+    }
+    for (int q = warp0; q < n_rows; q += nwarps) {
+        const int bn = q / HW, hw = q - bn * HW;
+        int pos[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int d = lane + 32 * r;
+            pos[r] = INT_MAX;
+            if (d < D) {
+                const int v = __ldg(pt2pos + ((int64_t)bn * D + d) * HW + hw);
+                if (v >= 0) pos[r] = v;
+            }
+        }
+        int rank[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rank[r] = 0;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const int other = __shfl_sync(0xffffffffu, pos[rr], l);
+#pragma unroll
+                for (int r = 0; r < R; ++r) rank[r] += (other < pos[r]) ? 1 : 0;
+            }
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (pos[r] != INT_MAX) {
+                const int64_t e = (int64_t)q * D + rank[r];
+                ent_p[e] = (bn * D + lane + 32 * r) * HW + hw;
+                ent_iv[e] = __ldg(pos2iv + pos[r]);
+                ++cnt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) { starts[q] = q * D; lengths[q] = cnt; ids[q] = q; }
+    }
+}
+
+// Generic build, last step: sorted forward positions -> (depth index, forward interval) entries.
+__global__ void __launch_bounds__(256) bwd_plan_fill_entries_kernel(const int32_t *__restrict__ pos,
+                                                                    const int32_t *__restrict__ rd,
+                                                                    const int32_t *__restrict__ pos2iv,
+                                                                    const BwdPlanHeader *hdr, int64_t cap,
+                                                                    int32_t *ent_p, int32_t *ent_iv) {
+    const int64_t n = min((int64_t)max(hdr->totals[0], 0), cap);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int i = pos[j];
+        ent_p[j] = rd[i];
+        ent_iv[j] = pos2iv[i];
+    }
+}
+
 }  // namespace fo
 
 using namespace fo;
@@ -158,63 +237,33 @@ using namespace fo;
 // C ABI
 // =================================================================================================
 extern "C" size_t fo_fwd_plan_bytes(int64_t n_voxels_total, int64_t n_points_capacity) {
-    if (n_voxels_total < 0 || n_points_capacity < 0) return 0;
-    // upper bound on tiles: every sample may add one partial tile; callers pass B*Z*Y*X so use a
-    // conservative bound of n_vox/kTile + (number of samples <= n_vox) ... bounded by n_vox itself.
-    const int64_t n_tiles_max = n_voxels_total / kTile + 4096 + 1;
-    return (size_t)(256 + fwd_plan_tile_bytes(n_tiles_max) + align_up(n_points_capacity * 4, 256));
+    if (n_voxels_total < 1 || n_points_capacity < 0) return 0;
+    return fwd_plan_bytes_for(n_voxels_total, n_points_capacity);
 }
 
-static int check_fwd_plan(size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points_cap, int64_t *n_tiles_out,
-                          int *tps_out) {
-    const int64_t tps = tiles_per_sample(n_vox);
-    const int64_t n_tiles = tps * B;
+namespace {
+// shared checks for entry points that take a forward plan
+int open_fwd_plan(void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points, FwdPlanView *pv,
+                  int64_t *n_tiles, int *tps) {
+    FO_CHECK_ARG(plan != nullptr, "forward plan is NULL");
     FO_CHECK_ARG(B >= 1 && n_vox >= 1, "B=%d and n_voxels_per_sample=%lld must be positive", B, (long long)n_vox);
     FO_CHECK_ARG((int64_t)B * n_vox < INT_MAX, "B*Z*Y*X = %lld does not fit int32 ranks", (long long)B * n_vox);
     FO_CHECK_ARG(B <= 4096, "B=%d exceeds the plan's sample bound (4096)", B);
-    const size_t need = 256 + fwd_plan_tile_bytes(n_tiles) + (size_t)align_up(n_points_cap * 4, 256);
-    if (plan_bytes < need)
-        return set_error(FO_ERR_SCRATCH, "forward plan buffer is %zu bytes, need %zu", plan_bytes, need);
-    *n_tiles_out = n_tiles;
-    *tps_out = (int)tps;
+    FO_CHECK_ARG(((uintptr_t)plan & 255) == 0, "forward plan must be 256-byte aligned");
+    if (!fwd_plan_view(plan, (int64_t)B * n_vox, plan_bytes, pv) || pv->p_cap < n_points)
+        return set_error(FO_ERR_SCRATCH, "forward plan buffer is %zu bytes, need %zu for %lld points", plan_bytes,
+                         fwd_plan_bytes_for((int64_t)B * n_vox, n_points), (long long)n_points);
+    *tps = (int)tiles_per_sample(n_vox);
+    *n_tiles = (int64_t)(*tps) * B;
     return FO_OK;
 }
 
-extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, const int32_t *interval_starts,
-                                 const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
-                                 const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, void *plan,
-                                 size_t plan_bytes) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    FO_CHECK_ARG(plan != nullptr, "plan is NULL");
-    FO_CHECK_ARG(n_points >= 0 && n_intervals >= 0 && n_points < INT_MAX, "negative or oversized counts");
-    FO_CHECK_ARG(n_intervals == 0 || (ranks_bev && interval_starts && interval_lengths), "NULL index array");
-    int64_t n_tiles; int tps;
-    if (int rc = check_fwd_plan(plan_bytes, B, n_vox, n_points, &n_tiles, &tps)) return rc;
-    FwdPlanView pv = fwd_plan_view(plan, n_tiles);
-    init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_tiles, tps, (int)n_intervals);
-    FO_LAUNCH_CHECK("init_fwd_header_kernel");
-    const int64_t work = n_intervals > n_tiles + 1 ? n_intervals : n_tiles + 1;
-    const int blocks = (int)((work + 255) / 256 > 148 * 16 ? 148 * 16 : (work + 255) / 256);
-    plan_from_intervals_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, stream>>>(
-        ranks_bev, interval_starts, interval_lengths, n_points, n_intervals, n_intervals_dev, n_vox,
-        (int64_t)B * n_vox, tps, (int)n_tiles, pv.hdr, pv.tile_off, pv.pos2iv);
-    FO_LAUNCH_CHECK("plan_from_intervals_kernel");
-    return FO_OK;
-}
-
-// ---- shared scratch layout of one bucket sort: [cnt | scan_state | counter] zeroed, then the rest
-namespace {
 struct SortScratch {
     int32_t *cnt;
     unsigned long long *state;
     int32_t *counter;
     size_t zero_bytes;
-    char *rest;
 };
-size_t sort_zero_bytes(int64_t n_buckets) {
-    const int64_t n_scan_tiles = (n_buckets + kScanTile - 1) / kScanTile;
-    return (size_t)(align_up(n_buckets * 4, 256) + align_up(n_scan_tiles * 8, 256) + 256);
-}
 SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     const int64_t n_scan_tiles = (n_buckets + kScanTile - 1) / kScanTile;
     SortScratch s;
@@ -223,22 +272,43 @@ SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     s.state = (unsigned long long *)p;          p += align_up(n_scan_tiles * 8, 256);
     s.counter = (int32_t *)p;                   p += 256;
     s.zero_bytes = (size_t)(p - (char *)base);
-    s.rest = p;
     return s;
 }
-int grid_for(int64_t work_items, int per_block) {
-    int64_t b = (work_items + per_block - 1) / per_block;
-    const int64_t cap = 148 * 8;               // persistent-ish: 8 CTAs of 256 threads per SM
-    if (b > cap) b = cap;
-    return b < 1 ? 1 : (int)b;
-}
+static_assert(kScanTile == 4096, "bucket_zero_bytes() in common.cuh assumes 4096-bucket scan tiles");
 }  // namespace
+
+// exported for the other translation units
+namespace fo {
+int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
+                        FwdPlanView *pv, int64_t *n_tiles, int *tps) {
+    return open_fwd_plan(const_cast<void *>(plan), plan_bytes, B, n_vox, n_points, pv, n_tiles, tps);
+}
+}  // namespace fo
+
+extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, const int32_t *interval_starts,
+                                 const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
+                                 const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, void *plan,
+                                 size_t plan_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FO_CHECK_ARG(n_points >= 0 && n_intervals >= 0 && n_points < INT_MAX, "negative or oversized counts");
+    FO_CHECK_ARG(n_intervals == 0 || (ranks_bev && interval_starts && interval_lengths), "NULL index array");
+    FwdPlanView pv; int64_t n_tiles; int tps;
+    if (int rc = open_fwd_plan(plan, plan_bytes, B, n_vox, n_points, &pv, &n_tiles, &tps)) return rc;
+    FO_CHECK_ARG(n_intervals <= pv.iv_cap, "n_intervals=%lld exceeds the plan's interval capacity %lld",
+                 (long long)n_intervals, (long long)pv.iv_cap);
+    init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_tiles, tps, (int)n_intervals);
+    FO_LAUNCH_CHECK("init_fwd_header_kernel");
+    const int64_t work = n_intervals > n_tiles + 1 ? n_intervals : n_tiles + 1;
+    plan_from_intervals_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
+        ranks_bev, interval_starts, interval_lengths, n_points, n_intervals, n_intervals_dev, n_vox,
+        (int64_t)B * n_vox, tps, (int)n_tiles, pv.hdr, pv.tile_off, pv.pos2iv, pv.iv_vox);
+    FO_LAUNCH_CHECK("plan_from_intervals_kernel");
+    return FO_OK;
+}
 
 extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total) {
     if (n_points_total < 0 || n_voxels_total < 0) return 0;
-    const int64_t cap_iv = n_points_total < n_voxels_total ? n_points_total : n_voxels_total;
-    return sort_zero_bytes(n_voxels_total) + (size_t)(2 * align_up(n_points_total * 4, 256) +
-                                                      align_up(cap_iv * 4, 256));
+    return bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256);
 }
 
 extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B, int32_t N, int32_t D, int32_t H,
@@ -252,7 +322,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     FO_CHECK_ARG(coor && lower_bound && interval, "NULL geometry input");
     FO_CHECK_ARG(ranks_bev && ranks_depth && ranks_feat && interval_starts && interval_lengths && counts_dev,
                  "NULL output array");
-    FO_CHECK_ARG(scratch != nullptr, "scratch is NULL");
+    FO_CHECK_ARG(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "scratch must be non-NULL, 256-byte aligned");
     FO_CHECK_ARG(((uintptr_t)coor & 15) == 0, "coor must be 16-byte aligned");
     const int64_t pps = (int64_t)N * D * H * W;
     const int64_t P = pps * B;
@@ -263,18 +333,13 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     const size_t need = fo_rank_prepare_scratch_bytes(P, NV);
     if (scratch_bytes < need)
         return set_error(FO_ERR_SCRATCH, "rank scratch is %zu bytes, need %zu", scratch_bytes, need);
+    FwdPlanView pv; int64_t n_tiles; int tps;
+    if (int rc = open_fwd_plan(fwd_plan, fwd_plan_bytes, B, n_vox, P, &pv, &n_tiles, &tps)) return rc;
 
     SortScratch ss = sort_scratch_view(scratch, NV);
-    int32_t *key = (int32_t *)ss.rest;
-    int32_t *slot = (int32_t *)(ss.rest + align_up(P * 4, 256));
-    int32_t *iv_bucket = (int32_t *)(ss.rest + 2 * align_up(P * 4, 256));
+    int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
+    int32_t *key = pv.pt2pos;                    // voxel id / -1 now, sorted position / -1 after the order pass
 
-    FwdPlanView pv{nullptr, nullptr, nullptr};
-    int64_t n_tiles = 0; int tps = 0;
-    if (fwd_plan) {
-        if (int rc = check_fwd_plan(fwd_plan_bytes, B, n_vox, P, &n_tiles, &tps)) return rc;
-        pv = fwd_plan_view(fwd_plan, n_tiles);
-    }
     FO_CUDA(cudaMemsetAsync(scratch, 0, ss.zero_bytes, stream));
     FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
 
@@ -290,7 +355,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
 
     ScanArgs sa;
     sa.cnt = ss.cnt; sa.n_buckets = NV;
-    sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = iv_bucket;
+    sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = pv.iv_vox;
     sa.totals = counts_dev;
     sa.tile_off = pv.tile_off; sa.vox_per_sample = n_vox; sa.tiles_per_sample = tps; sa.n_tiles = (int)n_tiles;
     sa.fwd_hdr = pv.hdr; sa.bwd_hdr = nullptr;
@@ -304,88 +369,93 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
 
     OrderArgs oa;
     oa.sorted = ranks_depth; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
-    oa.iv_bucket = iv_bucket; oa.n_intervals = counts_dev + 1;
-    oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev; oa.pos2iv = pv.pos2iv;
+    oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
+    oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev; oa.pos2iv = pv.pos2iv; oa.pt2pos = pv.pt2pos;
     oa.dhw = D * H * W; oa.hw = H * W;
     const int64_t cap_iv = P < NV ? P : NV;
-    if (pv.pos2iv)
-        order_segments_kernel<true><<<grid_for(cap_iv, kSortThreads), kSortThreads, 0, stream>>>(oa);
-    else
-        return set_error(FO_ERR_INVALID_ARG, "fo_rank_prepare needs a forward plan buffer (fwd_plan is NULL)");
+    order_segments_kernel<true><<<grid_for(cap_iv, kSortThreads, 16), kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_segments_kernel<fwd>");
     return FO_OK;
 }
 
-// ---- backward plan: [header(64) pad to 256 | bwd_pos[n_pts] | starts[n_rows] | lengths[n_rows] |
-//                      bucket_ids[n_rows] | sort scratch (cnt/state/counter) | slot[n_pts]]
-namespace {
-struct BwdLayout {
-    BwdPlanHeader *hdr;
-    int32_t *pos, *starts, *lengths, *ids;
-    void *sort_base;
-    int32_t *slot;
-    size_t total;
-};
-BwdLayout bwd_layout(void *base, int64_t n_pts, int64_t n_rows) {
-    BwdLayout L;
-    char *p = (char *)base;
-    L.hdr = (BwdPlanHeader *)p;        p += 256;
-    L.pos = (int32_t *)p;              p += align_up(n_pts * 4, 256);
-    L.starts = (int32_t *)p;           p += align_up(n_rows * 4, 256);
-    L.lengths = (int32_t *)p;          p += align_up(n_rows * 4, 256);
-    L.ids = (int32_t *)p;              p += align_up(n_rows * 4, 256);
-    L.sort_base = p;                   p += sort_zero_bytes(n_rows);
-    L.slot = (int32_t *)p;             p += align_up(n_pts * 4, 256);
-    L.total = (size_t)(p - (char *)base);
-    return L;
-}
-}  // namespace
-
 extern "C" size_t fo_bwd_plan_bytes(int64_t n_points_capacity, int64_t n_feat_rows) {
-    if (n_points_capacity < 0 || n_feat_rows < 0) return 0;
-    return bwd_layout(nullptr, n_points_capacity, n_feat_rows).total;
+    if (n_points_capacity < 0 || n_feat_rows < 1) return 0;
+    return bwd_plan_bytes_for(n_points_capacity, n_feat_rows);
 }
 
-__global__ void init_bwd_header_kernel(BwdPlanHeader *hdr) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { hdr->n_bwd_intervals = 0; hdr->n_points = 0; }
-}
-
-extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_feat, int64_t n_points,
-                                 const int32_t *n_points_dev, int64_t n_feat_rows, void *plan, size_t plan_bytes) {
+extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth, const int32_t *ranks_feat,
+                                 int64_t n_points, const int32_t *n_points_dev, int64_t n_depth,
+                                 int64_t n_feat_rows, int32_t hw, int32_t flags, const void *fwd_plan,
+                                 size_t fwd_plan_bytes, int32_t B, int64_t n_vox, void *plan, size_t plan_bytes) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    FO_CHECK_ARG(plan != nullptr, "plan is NULL");
-    FO_CHECK_ARG(n_points >= 0 && n_points < INT_MAX && n_feat_rows >= 1 && n_feat_rows < INT_MAX,
+    FO_CHECK_ARG(plan != nullptr && ((uintptr_t)plan & 255) == 0, "backward plan must be non-NULL, 256-byte aligned");
+    FO_CHECK_ARG(n_points >= 0 && n_points < INT_MAX && n_feat_rows >= 1 && n_feat_rows < INT_MAX && n_depth >= 0,
                  "bad sizes n_points=%lld n_feat_rows=%lld", (long long)n_points, (long long)n_feat_rows);
-    FO_CHECK_ARG(n_points == 0 || ranks_feat, "ranks_feat is NULL");
-    BwdLayout L = bwd_layout(plan, n_points, n_feat_rows);
-    if (plan_bytes < L.total)
-        return set_error(FO_ERR_SCRATCH, "backward plan buffer is %zu bytes, need %zu", plan_bytes, L.total);
-    SortScratch ss = sort_scratch_view(L.sort_base, n_feat_rows);
-    FO_CUDA(cudaMemsetAsync(L.sort_base, 0, ss.zero_bytes, stream));
-    init_bwd_header_kernel<<<1, 32, 0, stream>>>(L.hdr);
-    FO_LAUNCH_CHECK("init_bwd_header_kernel");
+    FwdPlanView fv; int64_t n_tiles; int tps;
+    if (int rc = open_fwd_plan_const(fwd_plan, fwd_plan_bytes, B, n_vox, n_points, &fv, &n_tiles, &tps)) return rc;
+    BwdPlanView bv;
+    const bool structured = (flags & FO_BWD_PLAN_STRUCTURED) != 0;
+    const int64_t need_cap = structured ? n_depth : n_points;
+    if (!bwd_plan_view(plan, n_feat_rows, plan_bytes, &bv) || bv.cap < need_cap)
+        return set_error(FO_ERR_SCRATCH, "backward plan buffer is %zu bytes, need %zu", plan_bytes,
+                         bwd_plan_bytes_for(need_cap, n_feat_rows));
+    if (structured) {
+        FO_CHECK_ARG(hw >= 1 && n_feat_rows % hw == 0 && n_depth % n_feat_rows == 0,
+                     "structured plan needs n_depth = n_feat_rows * D and n_feat_rows = B*N*hw");
+        const int D = (int)(n_depth / n_feat_rows);
+        FO_CHECK_ARG(n_depth <= fv.p_cap, "forward plan holds %lld points, structured build needs %lld",
+                     (long long)fv.p_cap, (long long)n_depth);
+        const int R = (D + 31) / 32;
+        if (R > 8) return set_error(FO_ERR_UNSUPPORTED, "structured backward plan supports D <= 256 (got %d)", D);
+        const int blocks = grid_for(n_feat_rows * 32, 256, 8);
+#define FO_STRUCT(RR)                                                                                         \
+    bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2pos, fv.pos2iv, D, hw, (int)n_feat_rows, \
+                                                              bv.hdr, bv.ent_p, bv.ent_iv, bv.starts,        \
+                                                              bv.lengths, bv.ids, n_points_dev)
+        switch (R) {
+            case 1: FO_STRUCT(1); break;
+            case 2: FO_STRUCT(2); break;
+            case 3: FO_STRUCT(3); break;
+            case 4: FO_STRUCT(4); break;
+            case 5: FO_STRUCT(5); break;
+            case 6: FO_STRUCT(6); break;
+            case 7: FO_STRUCT(7); break;
+            default: FO_STRUCT(8); break;
+        }
+#undef FO_STRUCT
+        FO_LAUNCH_CHECK("bwd_plan_structured_kernel");
+        return FO_OK;
+    }
+    // generic build: stable bucket sort of forward positions by ranks_feat
+    FO_CHECK_ARG(n_points == 0 || (ranks_feat && ranks_depth), "ranks_depth / ranks_feat is NULL");
+    SortScratch ss = sort_scratch_view(bv.counters, n_feat_rows);
+    FO_CUDA(cudaMemsetAsync(bv.counters, 0, ss.zero_bytes, stream));
+    FO_CUDA(cudaMemsetAsync(bv.hdr, 0, sizeof(BwdPlanHeader), stream));
     if (n_points == 0) return FO_OK;
     count_keys_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(ranks_feat, n_points, n_points_dev, n_feat_rows,
-                                                                   ss.cnt, L.slot);
+                                                                   ss.cnt, bv.slot, bv.hdr);
     FO_LAUNCH_CHECK("count_keys_kernel");
     ScanArgs sa;
     sa.cnt = ss.cnt; sa.n_buckets = n_feat_rows;
-    sa.iv_starts = L.starts; sa.iv_lengths = L.lengths; sa.iv_bucket = L.ids;
-    sa.totals = &L.hdr->reserved[0];
+    sa.iv_starts = bv.starts; sa.iv_lengths = bv.lengths; sa.iv_bucket = bv.ids;
+    sa.totals = bv.hdr->totals;
     sa.tile_off = nullptr; sa.vox_per_sample = 1; sa.tiles_per_sample = 0; sa.n_tiles = 0;
-    sa.fwd_hdr = nullptr; sa.bwd_hdr = L.hdr;
+    sa.fwd_hdr = nullptr; sa.bwd_hdr = bv.hdr;
     sa.state = ss.state; sa.tile_counter = ss.counter;
     const int scan_blocks = (int)((n_feat_rows + kScanTile - 1) / kScanTile);
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
-    place_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(ranks_feat, L.slot, ss.cnt, n_points, n_points_dev,
-                                                              n_feat_rows, L.pos);
+    place_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(ranks_feat, bv.slot, ss.cnt, n_points, n_points_dev,
+                                                              n_feat_rows, bv.pos);
     FO_LAUNCH_CHECK("place_kernel");
     OrderArgs oa;
-    oa.sorted = L.pos; oa.iv_starts = L.starts; oa.iv_lengths = L.lengths; oa.iv_bucket = nullptr;
-    oa.n_intervals = &L.hdr->n_bwd_intervals;
-    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.pos2iv = nullptr; oa.dhw = 1; oa.hw = 1;
-    order_segments_kernel<false><<<grid_for(n_feat_rows, kSortThreads), kSortThreads, 0, stream>>>(oa);
+    oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
+    oa.n_intervals = &bv.hdr->n_bwd_intervals;
+    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.pos2iv = nullptr; oa.pt2pos = nullptr; oa.dhw = 1; oa.hw = 1;
+    order_segments_kernel<false><<<grid_for(n_feat_rows, kSortThreads, 16), kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_segments_kernel<bwd>");
+    bwd_plan_fill_entries_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(bv.pos, ranks_depth, fv.pos2iv, bv.hdr,
+                                                                              bv.cap, bv.ent_p, bv.ent_iv);
+    FO_LAUNCH_CHECK("bwd_plan_fill_entries_kernel");
     return FO_OK;
 }

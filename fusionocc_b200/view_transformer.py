@@ -79,6 +79,7 @@ def rank_prepare(coor: torch.Tensor, grid_lower_bound, grid_interval, grid_size_
             _p(plan_buf), plan_bytes, _p(scratch), sbytes), 'fo_rank_prepare')
     plan = VoxelPoolPlan(plan_buf, B, X * Y * Z, P, cap_iv, counts_dev=counts)
     plan.trusted = True
+    plan.structured_hw, plan.n_depth = H * W, P
     return ranks_bev, ranks_depth, ranks_feat, starts, lengths, counts, plan
 
 
@@ -182,6 +183,7 @@ class LSSViewTransformer(_Base):
         # hand the plan to the op: a following bev_pool_v2(...) on these very tensors finds it cached
         exact = VoxelPoolPlan(plan.fwd, plan.B, plan.n_vox, n_kept, n_iv)
         exact.trusted = True
+        exact.structured_hw, exact.n_depth = plan.structured_hw, plan.n_depth
         key = (id(rb), id(st), id(ln), id(rf), plan.B, plan.n_vox)
         ver = (rb._version, st._version, ln._version, rf._version, rb.data_ptr(), st.data_ptr(), ln.data_ptr())
         _PLAN_CACHE[key] = (exact, ver, (rb, st, ln, rf))

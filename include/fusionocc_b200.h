@@ -113,12 +113,23 @@ int fo_bev_pool_v2_forward(fo_stream_t stream, int32_t c,
 /* ------------------------------------------------------------------------------------------------
  * Backward plan = the inverse interval ordering: forward positions regrouped by ranks_feat (stable),
  * i.e. the arrays the reference rebuilds with argsort / where on every backward
- * (bev_pool.py:47-57).  Depends only on ranks_feat; cache it with the forward plan.
+ * (bev_pool.py:47-57), stored as (depth index, forward interval) entries per image pixel.  Depends only
+ * on the index arrays; cache it with the forward plan.  Pass the SAME plan_bytes to every call that
+ * takes a plan buffer: the buffer layout is derived from it.
  * ------------------------------------------------------------------------------------------------ */
 size_t fo_bwd_plan_bytes(int64_t n_points_capacity, int64_t n_feat_rows);
 
-int fo_bwd_plan_build(fo_stream_t stream, const int32_t *ranks_feat,
-                      int64_t n_points, const int32_t *n_points_dev, int64_t n_feat_rows,
+/* flags of fo_bwd_plan_build */
+#define FO_BWD_PLAN_STRUCTURED 1  /* the forward plan was produced by fo_rank_prepare: every point p =
+                                     ((b*N+n)*D+d)*hw_size+hw belongs to feature row (b*N+n)*hw_size+hw and the
+                                     plan holds the point->position map, so the inverse ordering is built
+                                     per pixel in registers (no sort).  n_points_capacity must be >= n_depth. */
+
+int fo_bwd_plan_build(fo_stream_t stream, const int32_t *ranks_depth, const int32_t *ranks_feat,
+                      int64_t n_points, const int32_t *n_points_dev,
+                      int64_t n_depth, int64_t n_feat_rows, int32_t hw_size /* H*W, structured only */,
+                      int32_t flags,
+                      const void *fwd_plan, size_t fwd_plan_bytes, int32_t B, int64_t n_voxels_per_sample,
                       void *plan, size_t plan_bytes);
 
 /* ------------------------------------------------------------------------------------------------
@@ -129,6 +140,8 @@ int fo_bwd_plan_build(fo_stream_t stream, const int32_t *ranks_feat,
  * the reference's orders, so both are bit-identical to bev_pool_cuda.cu:91-120.
  *
  *   out_grad     fp32, layout `og_layout` (FO_LAYOUT_BCZYX is the gradient of bev_pool_v2()'s output)
+ *   n_points / n_intervals   capacities the plans were built with (live counts are in the plans)
+ *   fwd_plan / bwd_plan      the index arrays themselves are not needed: the plans carry everything
  *   scratch      fo_bwd_scratch_bytes() bytes (compact gathered out_grad rows when og is BCZYX)
  * ------------------------------------------------------------------------------------------------ */
 size_t fo_bwd_scratch_bytes(int64_t n_intervals_capacity, int32_t c, int32_t og_layout);
@@ -136,10 +149,7 @@ size_t fo_bwd_scratch_bytes(int64_t n_intervals_capacity, int32_t c, int32_t og_
 int fo_bev_pool_v2_backward(fo_stream_t stream, int32_t c,
                             const float *out_grad, int32_t og_layout,
                             const float *depth, const float *feat,
-                            const int32_t *ranks_depth, const int32_t *ranks_feat,
-                            const int32_t *ranks_bev,
-                            const int32_t *interval_starts, const int32_t *interval_lengths,
-                            int64_t n_points, int64_t n_intervals, const int32_t *n_counts_dev,
+                            int64_t n_points, int64_t n_intervals,
                             int32_t B, int64_t n_voxels_per_sample,
                             int64_t n_depth, int64_t n_feat_rows,
                             float *depth_grad, float *feat_grad,
