@@ -42,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 4 + 1 + 1 + 2     # rank_prepare, forward, bwd plan (structured), backward (memsets not counted)
+KERNELS_PER_STEP = 5 + 1 + 1 + 2     # rank_prepare, forward, bwd plan (structured), backward (memsets not counted)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -4,16 +4,15 @@
 // host sync, 164 MB out_grad.contiguous() un-permute) + src/bev_pool_cuda.cu:67-121 (ONE THREAD per
 // image pixel: 4 224 threads at the headline shape).  Here:
 //
-//   gather   (only when out_grad is (B,C,Z,Y,X)): a CTA per forward tile reads the C x 128 block with
-//            128-byte coalesced loads — predicated per lane on the tile's occupancy mask, so only the
-//            sectors that contain an occupied voxel are fetched — transposes it through shared memory
-//            and emits one compact channels-last row per interval: G[k, 0..C).  No 164 MB copy.
-//   pixel    an 8-lane group per backward interval (= image pixel) walks the pixel's points in the
-//            inverse interval ordering (backward plan entries: depth index + forward interval), eight
-//            points per batch so that each batch costs two memory round trips.  depth_grad[p] is the
-//            sequential FMA chain over c = 0..C-1 (handed lane to lane), feat_grad[q, :] the sequential
-//            FMA over the pixel's points: the reference's exact orders, no atomics, every output
-//            written once.
+//   gather   (only when out_grad is (B,C,Z,Y,X)): a warp per 32-voxel sub-tile reads the C x 32 block
+//            with 128-bit loads — predicated on the sub-tile's occupancy mask, so only the sectors that
+//            contain an occupied voxel are fetched — transposes it through shared memory and emits one
+//            compact channels-last row per interval: G[k, 0..C).  No 164 MB copy.
+//   pixel    one warp per backward interval (= image pixel) walks the pixel's points in the inverse
+//            interval ordering (backward plan entries: depth index + forward interval), 32 points per
+//            pass staged through shared memory.  depth_grad[p] is the sequential FMA chain over
+//            c = 0..C-1 run by one thread, feat_grad[q, :] the sequential FMA over the pixel's points:
+//            the reference's exact orders, no atomics, every output written once.
 #include "common.cuh"
 
 namespace fo {
@@ -23,75 +22,66 @@ struct GatherArgs {
     int32_t C;
     int64_t V;
     const FwdPlanHeader *hdr;
-    const int32_t *tile_off;
+    const int32_t *sub_iv;
     const int32_t *iv_vox;
     float *G;                       // [n_intervals, C]
 };
 
-template <int NCHUNK>
+// One warp per 32-voxel sub-tile (same tiling as the forward).  The C x 32 block of out_grad is read
+// with 128-bit loads, four full 128-byte lines per instruction, a 16-byte chunk being fetched only if
+// one of its four voxels is occupied (untouched sectors never leave HBM); it is staged in the
+// swizzled channel-major layout and one compact channels-last row G[k, 0..C) is emitted per interval.
 __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
-    extern __shared__ __align__(16) float stage[];      // [kTile][C+1]
-    __shared__ unsigned s_mask[kTile / 32];
-    __shared__ int s_vl[kTile];
-    const int tile = blockIdx.x;
-    const int k0 = a.tile_off[tile], k1 = a.tile_off[tile + 1];
-    if (k1 <= k0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = a.C, S = C + 1;
-    const int tps = a.hdr->tiles_per_sample;
-    const int b = tile / tps;
-    const int64_t v0 = (int64_t)(tile - b * tps) * kTile;
-    const int nv = (int)min((int64_t)kTile, a.V - v0);
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = a.C;
+    const int64_t u = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    if (u >= a.hdr->n_subs) return;
+    const int ia = __ldg(a.sub_iv + u), ib = __ldg(a.sub_iv + u + 1);
+    if (ib <= ia) return;
+    const int sps = a.hdr->subs_per_sample;
+    const int b = (int)(u / sps);
+    const int64_t v0 = (u - (int64_t)b * sps) << kSubShift;
+    const int nv = (int)min((int64_t)kSub, a.V - v0);
     const int64_t vbase = (int64_t)b * a.V + v0;
-    const int nk = min(k1 - k0, kTile);
+    const int ni = min(ib - ia, kSub);
+    float *stage = smem + (size_t)warp * C * kSub;
 
-    if (tid < kTile / 32) s_mask[tid] = 0u;
-    __syncthreads();
-    for (int kk = tid; kk < nk; kk += kThreads) {
-        int vl = (int)(__ldg(a.iv_vox + k0 + kk) - vbase);
-        if ((unsigned)vl >= (unsigned)nv) vl = -1;
-        s_vl[kk] = vl;
-        if (vl >= 0) atomicOr(&s_mask[vl >> 5], 1u << (vl & 31));
+    int my_v = -1;
+    if (lane < ni) {
+        my_v = (int)(__ldg(a.iv_vox + ia + lane) - vbase);
+        if ((unsigned)my_v >= (unsigned)nv) my_v = -1;
     }
-    __syncthreads();
-    {
-        const float *plane0 = a.og + ((int64_t)b * C) * a.V + v0;
-        unsigned m[kTile / 32];
+    const unsigned occ = __reduce_or_sync(0xffffffffu, my_v >= 0 ? (1u << my_v) : 0u);
+    const float *plane0 = a.og + ((int64_t)b * C) * a.V + v0;
+    if ((a.V & 3) == 0) {
+        const int row_in_quad = lane >> 3, chunk = lane & 7;
+        const bool want = ((occ >> (4 * chunk)) & 0xFu) != 0u;
+        float4 *stage4 = reinterpret_cast<float4 *>(stage);
+        for (int r0 = row_in_quad; r0 < C; r0 += 16) {
+            float4 v[4];
 #pragma unroll
-        for (int r = 0; r < kTile / 32; ++r) m[r] = s_mask[r];
-        for (int c = warp; c < C; c += kThreads / 32) {
-            const float *src = plane0 + (int64_t)c * a.V;
-            float v[kTile / 32];
+            for (int t = 0; t < 4; ++t) {
+                const int r = r0 + 4 * t;
+                v[t] = (want && r < C) ? __ldcs(reinterpret_cast<const float4 *>(plane0 + (int64_t)r * a.V) + chunk)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int r = 0; r < kTile / 32; ++r)
-                v[r] = ((m[r] >> lane) & 1u) ? __ldcs(src + lane + 32 * r) : 0.f;
-#pragma unroll
-            for (int r = 0; r < kTile / 32; ++r)
-                if ((m[r] >> lane) & 1u) stage[(lane + 32 * r) * S + c] = v[r];
-        }
-    }
-    __syncthreads();
-    if constexpr (NCHUNK > 0) {
-        const int g = tid / kGroupLanes, gl = tid % kGroupLanes, c4 = C >> 2;
-        for (int kk = g; kk < nk; kk += kGroupsPerCta) {
-            const int vl = s_vl[kk];
-            if (vl < 0) continue;
-            const float *row = stage + vl * S;
-            float *dst = a.G + (int64_t)(k0 + kk) * C;
-#pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                const int idx = gl + kGroupLanes * ch;
-                if (idx < c4)
-                    *reinterpret_cast<float4 *>(dst + 4 * idx) =
-                        make_float4(row[4 * idx], row[4 * idx + 1], row[4 * idx + 2], row[4 * idx + 3]);
+            for (int t = 0; t < 4; ++t) {
+                const int r = r0 + 4 * t;
+                if (want && r < C) stage4[r * (kSub / 4) + ((chunk ^ r) & 7)] = v[t];
             }
         }
     } else {
-        for (int kk = warp; kk < nk; kk += kThreads / 32) {
-            const int vl = s_vl[kk];
-            if (vl < 0) continue;
-            for (int c = lane; c < C; c += 32) a.G[(int64_t)(k0 + kk) * C + c] = stage[vl * S + c];
-        }
+        for (int c = 0; c < C; ++c)
+            if ((occ >> lane) & 1u) stage[stage_index(c, lane)] = __ldcs(plane0 + (int64_t)c * a.V + lane);
+    }
+    __syncwarp();
+    for (int l = 0; l < ni; ++l) {
+        const int v = __shfl_sync(0xffffffffu, my_v, l);
+        if (v < 0) continue;
+        float *dst = a.G + (int64_t)(ia + l) * C;
+        for (int c = lane; c < C; c += 32) dst[c] = stage[stage_index(c, v)];
     }
 }
 
@@ -111,89 +101,95 @@ struct PixelArgs {
 };
 
 constexpr int kPixThreads = 256;
+constexpr int kPixWarps   = kPixThreads / 32;
+constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 
-// One 8-lane group per backward interval.  NCHUNK >= 1: float4 lanes (C % 4 == 0).
-template <int NCHUNK>
+// One WARP per backward interval (= image pixel), points taken 32 at a time in the plan's order.
+//   stage   lane j fetches entry j (depth index, interval id) and its depth value; the 32 gathered
+//           out_grad rows are loaded four per instruction (8 lanes x float4 = one 128-byte row) into a
+//           per-warp shared-memory tile rows[32][C+4] (row stride C+4 keeps LDS.128 conflict-free).
+//   depth   lane j owns point j: depth_grad[p_j] = sum_c rows[j][c] * feat[q][c] as ONE sequential FMA
+//           chain over c = 0..C-1 in one thread (bev_pool_cuda.cu:96-101) — 2 LDS.128 + 4 FFMA per 4
+//           channels for 32 points at once.
+//   feat    lane c owns channel c (+32, +64 ...): feat_grad[q][c] = sum_j rows[j][c] * depth[p_j]
+//           sequentially over the pixel's points (bev_pool_cuda.cu:109-120); accumulators stay in
+//           registers across passes, so the order is exact for any number of points.
+// NACC = ceil(C / 32) feat accumulators per lane.  Vector path: C % 4 == 0.
+template <int NACC>
 __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
-    constexpr int kPixBatch = NCHUNK <= 2 ? 8 : 4;      // points per batch (register budget)
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (kGroupLanes - 1);
-    const unsigned gmask = 0xffu << (lane & 24);
-    const int gbase = lane & 24;
-    const int C = a.C, c4 = C >> 2;
+    extern __shared__ __align__(16) float psm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = a.C, c4 = C >> 2, S = C + 4;
+    float *rows = psm + (size_t)warp * (kPixChunk * S + C + kPixChunk);    // [32][S]
+    float *fs = rows + kPixChunk * S;                                       // feat row of the pixel [C]
+    float *ds = fs + C;                                                     // depth values of the pass [32]
     const int64_t n = a.n_bwd_dev ? min((int64_t)max(*a.n_bwd_dev, 0), a.n_bwd) : a.n_bwd;
-    const int64_t group0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kGroupLanes;
-    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / kGroupLanes;
-    const int last_owner = (c4 - 1) & (kGroupLanes - 1);
+    const int64_t warp0 = (int64_t)blockIdx.x * kPixWarps + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * kPixWarps;
+    const int sub = lane >> 3, gl = lane & 7;          // row-in-quad, 16-byte column group
 
-    for (int64_t m = group0; m < n; m += ngroups) {
+    for (int64_t m = warp0; m < n; m += nwarps) {
         const int s = __ldg(a.bwd_starts + m), len = __ldg(a.bwd_lengths + m);
         const int q = __ldg(a.bwd_ids + m);
         if (len <= 0 || s < 0 || (int64_t)s + len > a.n_entries || q < 0 || q >= a.n_feat_rows) continue;
-        float4 f[NCHUNK], fg[NCHUNK];
+        __syncwarp();
+        for (int i = lane; i < c4; i += 32)
+            reinterpret_cast<float4 *>(fs)[i] = ldg4(a.feat + ((int64_t)q * c4 + i) * 4);
+        float fg[NACC];
 #pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            const int idx = gl + kGroupLanes * ch;
-            f[ch] = (idx < c4) ? ldg4(a.feat + ((int64_t)q * c4 + idx) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            fg[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int j0 = 0; j0 < len; j0 += kPixBatch) {
-            // lane u of the group fetches the indices of point j0+u, then they are broadcast
+        for (int r = 0; r < NACC; ++r) fg[r] = 0.f;
+
+        for (int j0 = 0; j0 < len; j0 += kPixChunk) {
+            const int np = min(kPixChunk, len - j0);
             int my_p = -1, my_row = -1;
-            if (gl < kPixBatch && j0 + gl < len) {
-                my_p = __ldg(a.ent_p + s + j0 + gl);
-                const int iv = __ldg(a.ent_iv + s + j0 + gl);
+            if (lane < np) {
+                my_p = __ldg(a.ent_p + s + j0 + lane);
+                const int iv = __ldg(a.ent_iv + s + j0 + lane);
                 my_row = iv;
                 if (a.row_map) my_row = (iv >= 0 && iv < a.n_iv) ? __ldg(a.row_map + iv) : -1;
                 if (my_p < 0 || my_p >= a.n_depth || my_row < 0 || my_row >= a.n_rows_G) { my_p = -1; my_row = -1; }
             }
-            float my_d = (my_p >= 0) ? __ldg(a.depth + my_p) : 0.f;
-            float4 g[kPixBatch][NCHUNK];
-#pragma unroll
-            for (int u = 0; u < kPixBatch; ++u) {
-                const int row = __shfl_sync(gmask, my_row, gbase + u);
-#pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) {
-                    const int idx = gl + kGroupLanes * ch;
-                    g[u][ch] = (row >= 0 && idx < c4) ? ldg4(a.G + ((int64_t)row * c4 + idx) * 4)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float my_d = (my_p >= 0) ? __ldg(a.depth + my_p) : 0.f;
+            __syncwarp();                               // previous pass finished reading rows / ds
+            ds[lane] = my_d;
+            // gather: 4 rows per instruction
+            for (int r0 = 0; r0 < np; r0 += 4) {
+                const int row = __shfl_sync(0xffffffffu, my_row, r0 + sub);
+                for (int i = gl; i < c4; i += 8) {
+                    const float4 v = (row >= 0) ? ldg4(a.G + ((int64_t)row * c4 + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(rows + (r0 + sub) * S + 4 * i) = v;
                 }
             }
+            __syncwarp();
+            // depth grad: one thread, one sequential chain over all C channels
+            if (lane < np && my_p >= 0) {
+                const float4 *g4 = reinterpret_cast<const float4 *>(rows + lane * S);
+                const float4 *f4 = reinterpret_cast<const float4 *>(fs);
+                float sum = 0.f;
+                for (int i = 0; i < c4; ++i) {
+                    const float4 g = g4[i], f = f4[i];
+                    sum = fmaf(g.x, f.x, sum);
+                    sum = fmaf(g.y, f.y, sum);
+                    sum = fmaf(g.z, f.z, sum);
+                    sum = fmaf(g.w, f.w, sum);
+                }
+                a.depth_grad[my_p] = sum;
+            }
+            // feat grad: lane per channel, sequential over the points of this pass
 #pragma unroll
-            for (int u = 0; u < kPixBatch; ++u) {
-                const int p = __shfl_sync(gmask, my_p, gbase + u);
-                const float d = __shfl_sync(gmask, my_d, gbase + u);
-                if (j0 + u < len) {        // uniform across the group
-                    // feat grad: sequential over the pixel's points (bev_pool_cuda.cu:109-120)
-#pragma unroll
-                    for (int ch = 0; ch < NCHUNK; ++ch) fma4(fg[ch], g[u][ch], d);
-                    // depth grad: sequential FMA chain over c = 0..C-1 (bev_pool_cuda.cu:96-101)
-                    float sum = 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < NCHUNK; ++ch) {
-#pragma unroll
-                        for (int o = 0; o < kGroupLanes; ++o) {
-                            const int idx = ch * kGroupLanes + o;
-                            if (idx < c4) {
-                                if (idx > 0)
-                                    sum = __shfl_sync(gmask, sum, gbase + ((o + kGroupLanes - 1) & (kGroupLanes - 1)));
-                                if (gl == o) {
-                                    sum = fmaf(g[u][ch].x, f[ch].x, sum);
-                                    sum = fmaf(g[u][ch].y, f[ch].y, sum);
-                                    sum = fmaf(g[u][ch].z, f[ch].z, sum);
-                                    sum = fmaf(g[u][ch].w, f[ch].w, sum);
-                                }
-                            }
-                        }
-                    }
-                    if (gl == last_owner && p >= 0) a.depth_grad[p] = sum;
+            for (int r = 0; r < NACC; ++r) {
+                const int c = lane + 32 * r;
+                if (c < C) {
+                    float acc = fg[r];
+                    for (int j = 0; j < np; ++j) acc = fmaf(rows[j * S + c], ds[j], acc);
+                    fg[r] = acc;
                 }
             }
         }
 #pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            const int idx = gl + kGroupLanes * ch;
-            if (idx < c4) *reinterpret_cast<float4 *>(a.feat_grad + ((int64_t)q * c4 + idx) * 4) = fg[ch];
+        for (int r = 0; r < NACC; ++r) {
+            const int c = lane + 32 * r;
+            if (c < C) a.feat_grad[(int64_t)q * C + c] = fg[r];
         }
     }
 }
@@ -278,19 +274,29 @@ extern "C" size_t fo_bwd_scratch_bytes(int64_t n_intervals_capacity, int32_t c, 
 
 namespace {
 int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
-    const int64_t groups = pa.n_bwd;
-    if (groups <= 0) return FO_OK;
-    if (vec) {
-        const int blocks = grid_for(groups * kGroupLanes, kPixThreads, 16);
-        const int chunks = (pa.C / 4 + kGroupLanes - 1) / kGroupLanes;
-        switch (chunks) {
-            case 1: bwd_pixel_kernel<1><<<blocks, kPixThreads, 0, stream>>>(pa); break;
-            case 2: bwd_pixel_kernel<2><<<blocks, kPixThreads, 0, stream>>>(pa); break;
-            case 3: bwd_pixel_kernel<3><<<blocks, kPixThreads, 0, stream>>>(pa); break;
-            default: bwd_pixel_kernel<4><<<blocks, kPixThreads, 0, stream>>>(pa); break;
+    const int64_t pixels = pa.n_bwd;
+    if (pixels <= 0) return FO_OK;
+    const int C = pa.C;
+    const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C + kPixChunk) * sizeof(float);
+    const int nacc = (C + 31) / 32;
+    if (vec && nacc <= 4 && smem <= 200 * 1024) {
+        const int blocks = grid_for(pixels, kPixWarps, 8);
+#define FO_PIX(NA)                                                                                           \
+    do {                                                                                                     \
+        if (smem > 48 * 1024)                                                                                \
+            FO_CUDA(cudaFuncSetAttribute(bwd_pixel_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int)smem));                                                        \
+        bwd_pixel_kernel<NA><<<blocks, kPixThreads, smem, stream>>>(pa);                                     \
+    } while (0)
+        switch (nacc) {
+            case 1: FO_PIX(1); break;
+            case 2: FO_PIX(2); break;
+            case 3: FO_PIX(3); break;
+            default: FO_PIX(4); break;
         }
+#undef FO_PIX
     } else {
-        bwd_pixel_scalar_kernel<<<grid_for(groups * 32, kPixThreads, 16), kPixThreads, 0, stream>>>(pa);
+        bwd_pixel_scalar_kernel<<<grid_for(pixels * 32, kPixThreads, 16), kPixThreads, 0, stream>>>(pa);
     }
     FO_LAUNCH_CHECK("bwd_pixel_kernel");
     return FO_OK;
@@ -314,13 +320,12 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
     if (n_points == 0 || n_intervals == 0) return FO_OK;
     FO_CHECK_ARG(out_grad && depth && feat, "NULL input array");
     FO_CHECK_ARG(bwd_plan != nullptr, "backward plan is required");
-    FwdPlanView pv; int64_t n_tiles; int tps;
-    if (int rc = open_fwd_plan_const(fwd_plan, fwd_plan_bytes, B, n_vox, n_points, &pv, &n_tiles, &tps)) return rc;
+    FwdPlanView pv; int64_t n_subs; int sps;
+    if (int rc = open_fwd_plan_const(fwd_plan, fwd_plan_bytes, B, n_vox, n_points, &pv, &n_subs, &sps)) return rc;
     BwdPlanView bv;
     if (!bwd_plan_view(const_cast<void *>(bwd_plan), n_feat_rows, bwd_plan_bytes, &bv))
         return set_error(FO_ERR_SCRATCH, "backward plan buffer too small (%zu bytes)", bwd_plan_bytes);
-    const bool vec = (c % 4 == 0) && (c <= 4 * kGroupLanes * kMaxChunks) && (((uintptr_t)feat & 15) == 0) &&
-                     (((uintptr_t)feat_grad & 15) == 0);
+    const bool vec = (c % 4 == 0) && (((uintptr_t)feat & 15) == 0);
 
     PixelArgs pa;
     pa.depth = depth; pa.feat = feat;
@@ -335,28 +340,14 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
         if (!scratch || scratch_bytes < need)
             return set_error(FO_ERR_SCRATCH, "backward scratch is %zu bytes, need %zu", scratch_bytes, need);
         FO_CHECK_ARG(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
-        const size_t smem = (size_t)kTile * (c + 1) * sizeof(float);
+        const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
         if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
         GatherArgs ga;
         ga.og = out_grad; ga.C = c; ga.V = n_vox;
-        ga.hdr = pv.hdr; ga.tile_off = pv.tile_off; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
-        const bool gvec = (c % 4 == 0) && (c <= 4 * kGroupLanes * kMaxChunks);
-        const int chunks = gvec ? (c / 4 + kGroupLanes - 1) / kGroupLanes : 0;
-#define FO_GATHER(NC)                                                                                          \
-    do {                                                                                                       \
-        if (smem > 48 * 1024)                                                                                  \
-            FO_CUDA(cudaFuncSetAttribute(bwd_gather_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                         (int)smem));                                                          \
-        bwd_gather_kernel<NC><<<(int)n_tiles, kThreads, smem, stream>>>(ga);                                   \
-    } while (0)
-        switch (chunks) {
-            case 1: FO_GATHER(1); break;
-            case 2: FO_GATHER(2); break;
-            case 3: FO_GATHER(3); break;
-            case 4: FO_GATHER(4); break;
-            default: FO_GATHER(0); break;
-        }
-#undef FO_GATHER
+        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
+        if (smem > 48 * 1024)
+            FO_CUDA(cudaFuncSetAttribute(bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bwd_gather_kernel<<<(int)((n_subs + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, smem, stream>>>(ga);
         FO_LAUNCH_CHECK("bwd_gather_kernel");
         pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals;
     } else {

@@ -1,20 +1,20 @@
 // fusionocc_b200 — bev_pool_v2 forward (sm_100a).
 //
 // Reference: mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu:21-48 (kernel) + bev_pool.py:27 (82 MB
-// new_zeros) + bev_pool.py:91 (164 MB permute copy).  Here one kernel owns DENSE OUTPUT TILES: a CTA
-// takes 128 consecutive voxels of one sample, reduces the (few) intervals that land in them and writes
-// the whole C x 128 block — zeros included — once, already in (B,C,Z,Y,X) order.  HBM-bound: the
-// 81.92 MB/sample output is 94 % of the algorithmic bytes, so the design goal is a
-// single coalesced write stream with the gather work hidden under it.
+// new_zeros) + bev_pool.py:91 (164 MB permute copy).  Here one kernel owns the DENSE OUTPUT: every warp
+// takes a sub-tile of 32 consecutive voxels of one sample, reduces the points that land in it and writes
+// the whole C x 32 block — zeros included — once, already in (B,C,Z,Y,X) order.  HBM-bound by design:
+// the 81.92 MB/sample output is 94 % of the algorithmic bytes.
 //
-//   * 8 lanes x float4 cover 32 channels of one feature row with one 128-byte request; an 8-lane
-//     group walks an interval sequentially (psum = fmaf(feat, depth, psum) from +0.0f, in interval
-//     order: the reference's exact FFMA chain), 32 groups per CTA work on 32 intervals at once.
-//   * results are staged voxel-major in shared memory with an odd row stride (C+1), which makes the
-//     transposing read (lane <-> voxel) bank-conflict free; empty voxels are never staged — a 128-bit
-//     occupancy mask selects +0.0f.
-//   * the write-out is 128-byte-per-warp streaming stores (st.global.cs): each channel plane receives
-//     512 contiguous bytes per tile.
+//   * the sorted rank arrays keep a sub-tile's points contiguous, so the plan's sub_pt table gives the
+//     warp its point range and 32 points' (ranks_feat, ranks_depth, ranks_bev) arrive with three
+//     coalesced loads; the depth values with one gather;
+//   * lanes = channels: each point's 128-byte feature row is one coalesced load; the accumulator is the
+//     reference's exact FFMA chain (psum = fmaf(feat, depth, psum) from +0.0f, in point order); when the
+//     voxel id changes the finished accumulator is flushed to the warp's shared-memory stage;
+//   * the stage is the output block's own layout, [C][32] with an XOR-swizzled 16-byte chunk index, so
+//     the write-out is LDS.128 -> streaming STG.128, four full 128-byte lines per instruction;
+//   * no __syncthreads anywhere: 48 independent warps per SM hide the 3-round-trip dependency chain.
 #include "common.cuh"
 
 namespace fo {
@@ -31,143 +31,141 @@ struct FwdArgs {
     int64_t V;                      // voxels per sample
     float *out;
     const FwdPlanHeader *hdr;
-    const int32_t *tile_off;
-    const int32_t *iv_vox;          // voxel id of every interval (plan)
+    const int32_t *sub_pt;
 };
 
-// Sequential FMA over one interval, float4 per lane.  Points are taken in batches of four: all index
-// loads of a batch are issued together, then all value loads, then the four dependent FMA steps in
-// interval order — so an interval of length L costs 2*ceil(L/4) memory round trips, and the common
-// L <= 4 case exactly two.
-template <int NCHUNK>
-__device__ __forceinline__ void reduce_interval(float4 (&acc)[NCHUNK], const FwdArgs &a, int s, int len, int gl,
-                                                int c4 /* C/4 */) {
-#pragma unroll
-    for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < len; i += 4) {
-        int p[4], q[4];
-        float d[4];
-        float4 f[4][NCHUNK];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool ok = i + u < len;
-            p[u] = ok ? __ldg(a.rd + s + i + u) : -1;
-            q[u] = ok ? __ldg(a.rf + s + i + u) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool ok = p[u] >= 0;
-            d[u] = ok ? __ldg(a.depth + p[u]) : 0.f;
-#pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                const int idx = gl + kGroupLanes * ch;
-                f[u][ch] = (ok && idx < c4) ? ldg4(a.feat + ((int64_t)q[u] * c4 + idx) * 4)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (i + u < len) {
-#pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) fma4(acc[ch], f[u][ch], d[u]);
-            }
-        }
-    }
-}
+constexpr int kFwdUnroll = 4;       // feature rows in flight per lane
 
-// NCHUNK >= 1: vector path (C % 4 == 0, C <= 32*NCHUNK).  NCHUNK == 0: scalar path, any C.
-template <int NCHUNK, int LAYOUT>
+// NACC = ceil(C / 32) accumulators per lane; EXACT: C == 32 * NACC (no channel predicates).
+//
+// Instruction budget (the first versions of this kernel were ISSUE-bound, ~800 warp instructions per
+// sub-tile, profiles/r01): point records are broadcast through a per-warp shared-memory array (one
+// LDS.64 per point: no shuffles, hence no WARPSYNC sequences in the loop), feature-row addresses are
+// 32-bit, four rows are in flight per lane, and all index arithmetic is 32-bit.
+template <int NACC, bool EXACT, int LAYOUT>
 __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
-    extern __shared__ __align__(16) float stage[];      // [kTile][C+1]
-    __shared__ unsigned s_mask[kTile / 32];
-    if (a.hdr->flags & kFlagUnsorted) return;           // the order-agnostic path runs instead
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int2 s_rec[kWarpsPerCta][32 + kFwdUnroll];
+    if (a.hdr->flags & kFlagUnsorted) return;            // the order-agnostic path runs instead
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = a.C, S = C + 1;
-    const int tile = blockIdx.x;
-    const int tps = a.hdr->tiles_per_sample;
-    const int b = tile / tps;
-    const int64_t v0 = (int64_t)(tile - b * tps) * kTile;
-    const int nv = (int)min((int64_t)kTile, a.V - v0);
-    const int k0 = a.tile_off[tile], k1 = a.tile_off[tile + 1];
-    const int64_t vbase = (int64_t)b * a.V + v0;        // global voxel id of the tile's first voxel
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = EXACT ? 32 * NACC : a.C;
+    // CTA i -> sample i % B, four consecutive sub-tiles: the dense (near-ego) regions of all samples
+    // are reached at the same relative time instead of the last sample's trailing the whole grid
+    const int sps = a.hdr->subs_per_sample;
+    const int b = blockIdx.x % a.B;
+    const int su = (blockIdx.x / a.B) * kWarpsPerCta + warp;
+    if (su >= sps) return;
+    const int u = b * sps + su;
+    const int v0 = su << kSubShift;
+    const int nv = (int)min((int64_t)kSub, a.V - v0);
+    const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
+    const int vbase = (int)((int64_t)b * a.V) + v0;      // global voxel id of the sub-tile's first voxel (< 2^31)
+    const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((a.V & 3) == 0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *plane0 = a.out + ((int64_t)b * C) * a.V + v0;
+    const int row_in_quad = lane >> 3, chunk = lane & 7;
 
-    if (tid < kTile / 32) s_mask[tid] = 0u;
-    __syncthreads();
+    if (pa >= pb && vec_out) {                            // empty sub-tile: stream zeros, no staging
+        if (4 * chunk < nv) {
+            float *dst = plane0 + (int64_t)row_in_quad * a.V + 4 * chunk;
+            const int64_t step = 4 * a.V;
+            for (int r = row_in_quad; r < C; r += 4, dst += step) __stcs(reinterpret_cast<float4 *>(dst), zero4);
+        }
+        return;
+    }
+    float *stage = smem + warp * C * kSub;
+    float4 *stage4 = reinterpret_cast<float4 *>(stage);
+    for (int e = lane; e < C * (kSub / 4); e += 32) stage4[e] = zero4;
+    int2 *rec = s_rec[warp];
+    if (lane < kFwdUnroll) rec[32 + lane] = make_int2(0, 0);
 
-    if (k1 > k0) {
-        if constexpr (NCHUNK > 0) {
-            const int g = tid / kGroupLanes, gl = tid % kGroupLanes, c4 = C >> 2;
-            for (int k = k0 + g; k < k1; k += kGroupsPerCta) {
-                const int s = __ldg(a.starts + k), len = __ldg(a.lengths + k);
-                const int vl = (int)(__ldg(a.iv_vox + k) - vbase);
-                if ((unsigned)vl >= (unsigned)nv) continue;      // plan / arrays mismatch: never write outside the tile
-                float4 acc[NCHUNK];
-                reduce_interval<NCHUNK>(acc, a, s, len, gl, c4);
-                float *row = stage + vl * S;
+    float acc[NACC];
 #pragma unroll
-                for (int ch = 0; ch < NCHUNK; ++ch) {
-                    const int idx = gl + kGroupLanes * ch;
-                    if (idx < c4) {
-                        row[4 * idx + 0] = acc[ch].x; row[4 * idx + 1] = acc[ch].y;
-                        row[4 * idx + 2] = acc[ch].z; row[4 * idx + 3] = acc[ch].w;
-                    }
-                }
-                if (gl == 0) atomicOr(&s_mask[vl >> 5], 1u << (vl & 31));
+    for (int r = 0; r < NACC; ++r) acc[r] = 0.f;
+    int cur_v = -1;
+    for (int i0 = pa; i0 < pb; i0 += 32) {
+        const int n = min(32, pb - i0);
+        int2 mine = make_int2(0, 0);                      // (feature row << 5 | voxel in sub-tile, depth bits)
+        if (lane < n) {
+            const int q = __ldg(a.rf + i0 + lane);
+            const int v = __ldg(a.rb + i0 + lane) - vbase;
+            mine.x = (q << kSubShift) | (v & (kSub - 1));
+            mine.y = __float_as_int(__ldg(a.depth + __ldg(a.rd + i0 + lane)));
+        }
+        __syncwarp();
+        rec[lane] = mine;
+        __syncwarp();
+        for (int j = 0; j < n; j += kFwdUnroll) {
+            int2 r[kFwdUnroll];
+            float f[kFwdUnroll][NACC];
+#pragma unroll
+            for (int t = 0; t < kFwdUnroll; ++t) r[t] = rec[j + t];
+#pragma unroll
+            for (int t = 0; t < kFwdUnroll; ++t) {
+                const int row = (r[t].x >> kSubShift) * C + lane;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k)
+                    f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
             }
-        } else {
-            // scalar path: one warp per interval, lanes stride over channels
-            for (int k = k0 + warp; k < k1; k += kThreads / 32) {
-                const int s = __ldg(a.starts + k), len = __ldg(a.lengths + k);
-                const int vl = (int)(__ldg(a.iv_vox + k) - vbase);
-                if ((unsigned)vl >= (unsigned)nv) continue;
-                for (int c = lane; c < C; c += 32) {
-                    float psum = 0.f;
-                    for (int i = 0; i < len; ++i)
-                        psum = fmaf(__ldg(a.feat + (int64_t)__ldg(a.rf + s + i) * C + c),
-                                    __ldg(a.depth + __ldg(a.rd + s + i)), psum);
-                    stage[vl * S + c] = psum;
+#pragma unroll
+            for (int t = 0; t < kFwdUnroll; ++t) {
+                if (j + t < n) {                          // warp-uniform
+                    const int v = r[t].x & (kSub - 1);
+                    if (v != cur_v) {                     // warp-uniform: a new interval starts
+                        if (cur_v >= 0) {
+#pragma unroll
+                            for (int k = 0; k < NACC; ++k)
+                                if (EXACT || lane + 32 * k < C) stage[stage_index(lane + 32 * k, cur_v)] = acc[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+                        cur_v = v;
+                    }
+                    const float d = __int_as_float(r[t].y);
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d, acc[k]);
                 }
-                if (lane == 0) atomicOr(&s_mask[vl >> 5], 1u << (vl & 31));
             }
         }
     }
-    __syncthreads();
+    if (cur_v >= 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+            if (EXACT || lane + 32 * k < C) stage[stage_index(lane + 32 * k, cur_v)] = acc[k];
+    }
+    __syncwarp();
 
     if (LAYOUT == FO_LAYOUT_BCZYX) {
-        // warp w owns channels w, w+8, ...; lane <-> voxel: bank = (vl*(C+1) + c) % 32 = (vl + c) % 32
-        float *plane0 = a.out + ((int64_t)b * C) * a.V + v0;
-        unsigned m[kTile / 32];
-#pragma unroll
-        for (int r = 0; r < kTile / 32; ++r) m[r] = s_mask[r];
-        for (int c = warp; c < C; c += kThreads / 32) {
-            float *dst = plane0 + (int64_t)c * a.V;
-#pragma unroll
-            for (int r = 0; r < kTile / 32; ++r) {
-                const int vl = lane + 32 * r;
-                if (vl < nv) {
-                    const float val = ((m[r] >> lane) & 1u) ? stage[vl * S + c] : 0.f;
-                    st_stream(dst + vl, val);
-                }
+        if (vec_out) {
+            // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction
+            for (int r = row_in_quad; r < C; r += 4) {
+                const int ck = (chunk ^ r) & 7;                       // logical chunk stored at position `chunk`
+                if (4 * ck < nv)
+                    __stcs(reinterpret_cast<float4 *>(plane0 + (int64_t)r * a.V + 4 * ck), stage4[r * (kSub / 4) + chunk]);
+            }
+        } else {
+            for (int e = lane; e < C * kSub; e += 32) {
+                const int c = e >> kSubShift, v = e & (kSub - 1);
+                if (v < nv) __stcs(plane0 + (int64_t)c * a.V + v, stage[stage_index(c, v)]);
             }
         }
     } else {
-        // (B,Z,Y,X,C): the tile is nv*C contiguous floats
-        float *dst = a.out + vbase * C;
-        const int n = nv * C;
-        for (int e = tid; e < n; e += kThreads) {
-            const int vl = e / C, c = e - vl * C;
-            const float val = ((s_mask[vl >> 5] >> (vl & 31)) & 1u) ? stage[vl * S + c] : 0.f;
-            st_stream(dst + e, val);
+        // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
+        float *dst = a.out + (int64_t)vbase * C;
+        for (int e = lane; e < nv * C; e += 32) {
+            const int v = e / C, c = e - v * C;
+            __stcs(dst + e, stage[stage_index(c, v)]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Order-agnostic path: guarded zero fill + interval scatter.  Used (a) when the plan found the
-// interval voxels unsorted / out of range, (b) by the source-compatible fo_compat_bev_pool_v2
-// (caller-zeroed (B,Z,Y,X,C) output, arbitrary interval order) and (c) for channel counts too large
-// for the staged tile.  Invalid intervals are skipped instead of writing out of bounds.
+// interval list not in canonical form (voxels not strictly increasing, intervals not back to back, or
+// out of range), (b) by the source-compatible fo_compat_bev_pool_v2 (caller-zeroed (B,Z,Y,X,C) output,
+// arbitrary interval order) and (c) for channel counts too large for the staged tile.  Invalid
+// intervals are skipped instead of writing out of bounds.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) zero_if_flag_kernel(float4 *out, int64_t n4, float *tail, int n_tail,
                                                            const FwdPlanHeader *hdr, int need_flag) {
@@ -208,23 +206,35 @@ __global__ void __launch_bounds__(256) fwd_scatter_kernel(FwdArgs a, int need_fl
 using namespace fo;
 
 namespace {
-template <int NCHUNK, int LAYOUT>
-int launch_dense(const FwdArgs &a, int n_tiles, size_t smem, cudaStream_t stream) {
-    auto kern = fwd_dense_kernel<NCHUNK, LAYOUT>;
+template <int NACC, bool EXACT, int LAYOUT>
+int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
+    auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_tiles, kThreads, smem, stream>>>(a);
+    kern<<<n_ctas, kThreads, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
     return FO_OK;
 }
 template <int LAYOUT>
-int launch_dense_any(const FwdArgs &a, int n_tiles, size_t smem, bool vec, cudaStream_t stream) {
-    const int chunks = vec ? (a.C / 4 + kGroupLanes - 1) / kGroupLanes : 0;
-    switch (chunks) {
-        case 1: return launch_dense<1, LAYOUT>(a, n_tiles, smem, stream);
-        case 2: return launch_dense<2, LAYOUT>(a, n_tiles, smem, stream);
-        case 3: return launch_dense<3, LAYOUT>(a, n_tiles, smem, stream);
-        case 4: return launch_dense<4, LAYOUT>(a, n_tiles, smem, stream);
-        default: return launch_dense<0, LAYOUT>(a, n_tiles, smem, stream);
+int launch_dense_any(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
+    const int nacc = (a.C + 31) / 32;
+    if (a.C % 32 == 0) {
+        switch (nacc) {
+            case 1: return launch_dense<1, true, LAYOUT>(a, n_ctas, smem, stream);
+            case 2: return launch_dense<2, true, LAYOUT>(a, n_ctas, smem, stream);
+            case 3: return launch_dense<3, true, LAYOUT>(a, n_ctas, smem, stream);
+            case 4: return launch_dense<4, true, LAYOUT>(a, n_ctas, smem, stream);
+            default: break;
+        }
+    }
+    switch (nacc) {
+        case 1: return launch_dense<1, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 2: return launch_dense<2, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 3: return launch_dense<3, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 4: return launch_dense<4, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 5: return launch_dense<5, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 6: return launch_dense<6, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 7: return launch_dense<7, false, LAYOUT>(a, n_ctas, smem, stream);
+        default: return launch_dense<8, false, LAYOUT>(a, n_ctas, smem, stream);
     }
 }
 }  // namespace
@@ -243,21 +253,23 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     FO_CHECK_ARG(n_points >= 0 && n_intervals >= 0 && n_points < INT_MAX, "negative or oversized counts");
     FO_CHECK_ARG(n_intervals == 0 || (depth && feat && ranks_depth && ranks_feat && ranks_bev && interval_starts &&
                                       interval_lengths), "NULL input array");
-    FwdPlanView pv; int64_t n_tiles; int tps;
-    if (int rc = open_fwd_plan_const(plan, plan_bytes, B, n_vox, n_points, &pv, &n_tiles, &tps)) return rc;
+    FwdPlanView pv; int64_t n_subs; int sps;
+    if (int rc = open_fwd_plan_const(plan, plan_bytes, B, n_vox, n_points, &pv, &n_subs, &sps)) return rc;
 
     FwdArgs a;
     a.depth = depth; a.feat = feat; a.rd = ranks_depth; a.rf = ranks_feat; a.rb = ranks_bev;
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = n_points; a.n_intervals = n_intervals; a.n_intervals_dev = n_intervals_dev;
-    a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.tile_off = pv.tile_off; a.iv_vox = pv.iv_vox;
+    a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.sub_pt = pv.sub_pt;
 
-    const size_t smem = (size_t)kTile * (c + 1) * sizeof(float);
-    const bool dense_ok = smem <= 200 * 1024;
-    const bool vec = (c % 4 == 0) && (c <= 4 * kGroupLanes * kMaxChunks) && (((uintptr_t)feat & 15) == 0);
+    const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
+    // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
+    const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_points < (1 << 26) &&
+                          (int64_t)B * n_vox * 1 < INT_MAX;
     if (dense_ok) {
-        int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, (int)n_tiles, smem, vec, stream)
-                                                 : launch_dense_any<FO_LAYOUT_BZYXC>(a, (int)n_tiles, smem, vec, stream);
+        const int n_ctas = (int)(((int64_t)sps + kWarpsPerCta - 1) / kWarpsPerCta) * B;
+        int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
+                                                 : launch_dense_any<FO_LAYOUT_BZYXC>(a, n_ctas, smem, stream);
         if (rc) return rc;
     }
     // order-agnostic path, guarded by the plan's flag on the device (no host sync); unconditional when
@@ -288,8 +300,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.depth = depth; a.feat = feat; a.rd = ranks_depth; a.rf = ranks_feat; a.rb = ranks_bev;
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
-    a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.tile_off = nullptr; a.iv_vox = nullptr;
-    int64_t blocks = ((int64_t)n_intervals * 32 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<(int)blocks, 256, 0, 0>>>(a, 0);
+    a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
+    fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

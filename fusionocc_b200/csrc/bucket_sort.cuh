@@ -9,9 +9,10 @@
 // bucket counter array (2.56 MB per sample at 200x200x16) lives in B200's 126 MB L2.
 //
 //   count    slot[i] = atomicAdd(&cnt[key_i], 1)                  (arrival order, arbitrary)
-//   scan     single-pass decoupled look-back exclusive scan of cnt, fused with run extraction:
-//            emits interval_starts / interval_lengths / bucket ids for non-empty buckets, the totals,
-//            and (forward flavour) the per-tile first-interval table of the forward plan
+//   scan     one-pass exclusive scan of cnt (tile aggregates come from the count pass, so CTAs are
+//            independent), fused with run extraction: emits interval_starts / interval_lengths / bucket
+//            ids for non-empty buckets, the totals, and (forward flavour) the per-tile first-interval
+//            table of the forward plan
 //   place    sorted[ cnt[key_i] + slot[i] ] = i
 //   order    every bucket's segment is sorted ascending => the result is exactly the STABLE sort
 //            (ties in ascending original index), independent of the atomics' arrival order
@@ -24,23 +25,43 @@ namespace fo {
 constexpr int kScanThreads = 256;
 constexpr int kScanItems   = 16;                          // buckets per thread (4 x int4)
 constexpr int kScanTile    = kScanThreads * kScanItems;   // 4096 buckets per CTA
+constexpr int kScanShift   = 12;
+static_assert((1 << kScanShift) == kScanTile, "scan tile shift");
 
-// Decoupled look-back descriptor: [63:62] status, [61:31] point sum, [30:0] non-empty-bucket count.
-constexpr unsigned long long kStEmpty = 0ull, kStAgg = 1ull, kStPrefix = 2ull;
-__device__ __forceinline__ unsigned long long desc_pack(unsigned long long st, unsigned pts, unsigned ne) {
-    return (st << 62) | ((unsigned long long)(pts & 0x7fffffffu) << 31) | (unsigned long long)(ne & 0x7fffffffu);
-}
-__device__ __forceinline__ unsigned desc_status(unsigned long long d) { return (unsigned)(d >> 62); }
-__device__ __forceinline__ unsigned desc_pts(unsigned long long d) { return (unsigned)((d >> 31) & 0x7fffffffu); }
-__device__ __forceinline__ unsigned desc_ne(unsigned long long d) { return (unsigned)(d & 0x7fffffffu); }
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// Per-scan-tile aggregates (points << 32 | non-empty buckets) come from a separate reduce pass over the
+// counter array (coalesced int4 reads, the array is L2-resident right after the count pass), so the scan
+// kernel needs no inter-CTA communication at all — no decoupled look-back, no spinning: CTA t sums
+// agg[0..t).  (Tried and rejected, profiles/r01: a decoupled look-back scan, 41 us, and aggregating with
+// one atomic per element inside the count pass, 157 us of same-address contention.)
+__global__ void __launch_bounds__(kScanThreads) tile_reduce_kernel(const int32_t *__restrict__ cnt, int64_t n_buckets,
+                                                                   unsigned long long *__restrict__ agg) {
+    __shared__ unsigned long long s_red[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems / 4; ++j) {
+        const int64_t i = base + ((int64_t)j * kScanThreads + tid) * 4;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i + 4 <= n_buckets) v = *reinterpret_cast<const int4 *>(cnt + i);
+        else {
+            if (i < n_buckets) v.x = cnt[i];
+            if (i + 1 < n_buckets) v.y = cnt[i + 1];
+            if (i + 2 < n_buckets) v.z = cnt[i + 2];
+        }
+        mine += ((unsigned long long)(unsigned)(v.x + v.y + v.z + v.w) << 32) |
+                (unsigned long long)((v.x > 0) + (v.y > 0) + (v.z > 0) + (v.w > 0));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) t += s_red[w];
+        agg[blockIdx.x] = t;
+    }
 }
 
 struct ScanArgs {
@@ -50,28 +71,28 @@ struct ScanArgs {
     int32_t *iv_lengths;
     int32_t *iv_bucket;
     int32_t *totals;         // totals[0] = number of points, totals[1] = number of non-empty buckets
-    // forward flavour: first-interval table per output tile (nullptr to skip)
-    int32_t *tile_off;
+    // forward flavour: first interval / first point of every 32-voxel sub-tile (nullptr to skip)
+    int32_t *sub_iv;
+    int32_t *sub_pt;
     int64_t  vox_per_sample;
-    int32_t  tiles_per_sample;
-    int32_t  n_tiles;
+    int32_t  subs_per_sample;
+    int32_t  n_subs;
     FwdPlanHeader *fwd_hdr;  // may be nullptr
     BwdPlanHeader *bwd_hdr;  // may be nullptr
-    unsigned long long *state;   // [ceil(n_buckets / kScanTile)] zero-initialised
-    int32_t *tile_counter;       // zero-initialised
+    const unsigned long long *agg;   // [ceil(n_buckets / kScanTile)] from the count pass
 };
 
-// One CTA = kScanTile consecutive buckets.  Tile ids are handed out by an atomic counter so that every
-// predecessor of a running tile has already started (forward-progress guarantee of the look-back).
+// One CTA = kScanTile consecutive buckets.
 __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) {
-    __shared__ int s_tile;
     __shared__ unsigned long long s_warp[kScanThreads / 32];
-    __shared__ unsigned long long s_prefix;     // exclusive prefix of this tile: (pts << 32) | ne
+    __shared__ unsigned long long s_red[kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1);
-    __syncthreads();
-    const int tile = s_tile;
+    const int tile = blockIdx.x;
     const int64_t base = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
+
+    // exclusive prefix of this tile = sum of the aggregates of all earlier tiles
+    unsigned long long pre = 0;
+    for (int t = tid; t < tile; t += kScanThreads) pre += a.agg[t];
 
     int c[kScanItems];
     if (base + kScanItems <= a.n_buckets) {
@@ -90,59 +111,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
     for (int j = 0; j < kScanItems; ++j)
         mine += ((unsigned long long)(unsigned)c[j] << 32) | (c[j] > 0 ? 1ull : 0ull);
 
-    // block-wide exclusive scan of `mine`
+    // block-wide exclusive scan of `mine`, block-wide sum of `pre`
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += n;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_red[warp] = pre;
     __syncthreads();
-    unsigned long long warp_off = 0, block_total = 0;
+    unsigned long long warp_off = 0, tile_prefix = 0;
 #pragma unroll
     for (int w = 0; w < kScanThreads / 32; ++w) {
-        unsigned long long t = s_warp[w];
-        if (w < warp) warp_off += t;
-        block_total += t;
+        if (w < warp) warp_off += s_warp[w];
+        tile_prefix += s_red[w];
     }
-    const unsigned blk_pts = (unsigned)(block_total >> 32), blk_ne = (unsigned)(block_total & 0xffffffffu);
-
-    if (warp == 0) {
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(a.state, desc_pack(kStPrefix, blk_pts, blk_ne));
-        } else {
-            if (lane == 0) st_relaxed_u64(a.state + tile, desc_pack(kStAgg, blk_pts, blk_ne));
-            int look = tile - 1;
-            while (true) {
-                const int idx = look - lane;
-                unsigned long long d = desc_pack(kStPrefix, 0, 0);      // virtual tile -1: empty inclusive prefix
-                if (idx >= 0) {
-                    do { d = ld_relaxed_u64(a.state + idx); } while (desc_status(d) == kStEmpty);
-                }
-                const unsigned pmask = __ballot_sync(0xffffffffu, desc_status(d) == kStPrefix);
-                const int first = pmask ? (__ffs(pmask) - 1) : 31;
-                unsigned long long contrib = (lane <= first) ? (((unsigned long long)desc_pts(d) << 32) | desc_ne(d)) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                excl += contrib;
-                if (pmask) break;
-                look -= 32;
-            }
-            if (lane == 0)
-                st_relaxed_u64(a.state + tile, desc_pack(kStPrefix, (unsigned)(excl >> 32) + blk_pts,
-                                                         (unsigned)(excl & 0xffffffffu) + blk_ne));
-        }
-        if (lane == 0) s_prefix = excl;
-    }
-    __syncthreads();
-    unsigned long long run = s_prefix + warp_off + (incl - mine);
+    unsigned long long run = tile_prefix + warp_off + (incl - mine);
     unsigned pts = (unsigned)(run >> 32), ne = (unsigned)(run & 0xffffffffu);
 
     // position of this thread's first bucket inside its sample (for the tile table)
     int64_t vin = 0, sample = 0;
-    const bool want_tiles = a.tile_off != nullptr;
+    const bool want_tiles = a.sub_iv != nullptr;
     if (want_tiles) { sample = base / a.vox_per_sample; vin = base - sample * a.vox_per_sample; }
 
     int o[kScanItems];
@@ -152,8 +144,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
         o[j] = (int)pts;
         if (v < a.n_buckets) {
             if (want_tiles) {
-                if ((vin & (kTile - 1)) == 0)
-                    a.tile_off[sample * a.tiles_per_sample + (vin >> 7)] = (int)ne;
+                if ((vin & (kSub - 1)) == 0) {
+                    const int64_t u = sample * a.subs_per_sample + (vin >> kSubShift);
+                    a.sub_iv[u] = (int)ne;
+                    a.sub_pt[u] = (int)pts;
+                }
                 if (++vin == a.vox_per_sample) { vin = 0; ++sample; }
             }
             if (c[j] > 0) {
@@ -165,7 +160,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
             }
         }
     }
-    static_assert(kTile == 128, "tile shift above assumes 128");
     if (base + kScanItems <= a.n_buckets) {
         int4 *dst = reinterpret_cast<int4 *>(a.cnt + base);
 #pragma unroll
@@ -179,7 +173,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
     if (base <= a.n_buckets - 1 && a.n_buckets - 1 < base + kScanItems) {
         a.totals[0] = (int)pts;
         a.totals[1] = (int)ne;
-        if (want_tiles) a.tile_off[a.n_tiles] = (int)ne;
+        if (want_tiles) { a.sub_iv[a.n_subs] = (int)ne; a.sub_pt[a.n_subs] = (int)pts; }
         if (a.fwd_hdr) a.fwd_hdr->n_intervals = (int)ne;
         if (a.bwd_hdr) { a.bwd_hdr->n_bwd_intervals = (int)ne; a.bwd_hdr->n_points = (int)pts; }
     }
@@ -214,7 +208,30 @@ __device__ inline void warp_sort_segment(int32_t *seg, int len, int *smem /* kSo
         if (lane < len) seg[lane] = v;
         return;
     }
-    int n2 = 64;
+    if (len <= 128) {
+        // rank by counting in registers: all keys are distinct, so the rank of a key is the number of
+        // smaller keys (4 keys per lane, 128 broadcasts)
+        int v[4], rank[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { v[r] = (lane + 32 * r < len) ? seg[lane + 32 * r] : INT_MAX; rank[r] = 0; }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            if (32 * rr < len) {
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) {
+                    const int other = __shfl_sync(0xffffffffu, v[rr], l);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) rank[r] += (other < v[r]) ? 1 : 0;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (v[r] != INT_MAX) seg[rank[r]] = v[r];
+        return;
+    }
+    int n2 = 256;
     while (n2 < len) n2 <<= 1;
     if (n2 <= kSortSmem) {
         for (int i = lane; i < n2; i += 32) smem[i] = (i < len) ? seg[i] : INT_MAX;
@@ -269,6 +286,11 @@ struct OrderArgs {
     int32_t *pos2iv;
     int32_t *pt2pos;            // frustum point -> sorted position (its -1 entries were written by voxelise)
     int32_t dhw, hw;            // D*H*W and H*W: ranks_feat = (p / dhw) * hw + p % hw  (view_transformer.py:239-244)
+    // intervals longer than kLaneSortMax are queued here by the short pass and ordered, one warp each,
+    // by the long pass — dense near-ego voxels are consecutive in voxel order, so without the queue a
+    // few warps would inherit dozens of long intervals each (measured: 103 us -> tail-bound)
+    int32_t *long_list;
+    int32_t *long_count;        // zero-initialised
 };
 
 // 19-comparator optimal sorting network for 8 keys (ascending)
@@ -285,55 +307,57 @@ __device__ __forceinline__ void sort8(int (&v)[8]) {
 constexpr int kLaneSortMax = 8;   // intervals up to this length are ordered by one lane in registers
 
 template <bool kForward>
-__global__ void __launch_bounds__(kSortThreads) order_segments_kernel(OrderArgs a) {
-    __shared__ int s_sort[kSortThreads / 32][kSortSmem];
+__global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
     const int n = *a.n_intervals;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int s = a.iv_starts[k], len = a.iv_lengths[k];
+        if (len > kLaneSortMax) {
+            a.long_list[atomicAdd(a.long_count, 1)] = k;
+            continue;
+        }
+        const int bucket = kForward ? a.iv_bucket[k] : 0;
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
+        if (len > 1) sort8(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < len) {
+                if (len > 1) a.sorted[s + j] = v[j];
+                if (kForward) {
+                    a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
+                    a.ranks_bev[s + j] = bucket;
+                    a.pos2iv[s + j] = k;
+                    a.pt2pos[v[j]] = s + j;
+                }
+            }
+        }
+    }
+}
+
+template <bool kForward>
+__global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
+    __shared__ int s_sort[kSortThreads / 32][kSortSmem];
+    const int n = *a.long_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = (blockIdx.x * kSortThreads + warp * 32); base < n; base += gridDim.x * kSortThreads) {
-        const int k = base + lane;
-        int s = 0, len = 0, bucket = 0;
-        if (k < n) {
-            s = a.iv_starts[k];
-            len = a.iv_lengths[k];
-            if (kForward) bucket = a.iv_bucket[k];
-        }
-        if (len > 0 && len <= kLaneSortMax) {
-            int v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
-            if (len > 1) sort8(v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < len) {
-                    if (len > 1) a.sorted[s + j] = v[j];
-                    if (kForward) {
-                        a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
-                        a.ranks_bev[s + j] = bucket;
-                        a.pos2iv[s + j] = k;
-                        a.pt2pos[v[j]] = s + j;
-                    }
-                }
+    const int nwarps = gridDim.x * (kSortThreads / 32);
+    for (int w = blockIdx.x * (kSortThreads / 32) + warp; w < n; w += nwarps) {
+        const int k = a.long_list[w];
+        const int ls = a.iv_starts[k], ll = a.iv_lengths[k];
+        const int lb = kForward ? a.iv_bucket[k] : 0;
+        warp_sort_segment(a.sorted + ls, ll, s_sort[warp], lane);
+        __syncwarp();
+        if (kForward) {
+            for (int j = lane; j < ll; j += 32) {
+                const int p = a.sorted[ls + j];
+                a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                a.ranks_bev[ls + j] = lb;
+                a.pos2iv[ls + j] = k;
+                a.pt2pos[p] = ls + j;
             }
         }
-        unsigned longmask = __ballot_sync(0xffffffffu, len > kLaneSortMax);
-        while (longmask) {
-            const int src = __ffs(longmask) - 1;
-            longmask &= longmask - 1;
-            const int ls = __shfl_sync(0xffffffffu, s, src);
-            const int ll = __shfl_sync(0xffffffffu, len, src);
-            const int lb = __shfl_sync(0xffffffffu, bucket, src);
-            warp_sort_segment(a.sorted + ls, ll, s_sort[warp], lane);
-            __syncwarp();
-            if (kForward) {
-                for (int j = lane; j < ll; j += 32) {
-                    const int p = a.sorted[ls + j];
-                    a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
-                    a.ranks_bev[ls + j] = lb;
-                    a.pos2iv[ls + j] = base + src;
-                    a.pt2pos[p] = ls + j;
-                }
-            }
-        }
+        __syncwarp();
     }
 }
 

@@ -16,29 +16,31 @@ namespace fo {
 
 // ----------------------------------------------------------------------------------------------
 // Tiling constants shared by the forward plan, the forward kernel and the backward gather.
-// A tile is kTile consecutive voxels of ONE sample in flattened (z,y,x) order; in the (B,C,Z,Y,X)
-// output that is C contiguous runs of kTile floats (512 B each).
+// The unit of work is a SUB-TILE: kSub = 32 consecutive voxels of ONE sample in flattened (z,y,x)
+// order, owned by one warp; in the (B,C,Z,Y,X) tensor that is C runs of 128 contiguous bytes (one full
+// cache line each).  A CTA is four warps = four consecutive sub-tiles (512 contiguous bytes per channel
+// plane), with no block-level synchronisation at all.
 //
-// Sizing rule (measured, profiles/r01): a tile's critical path is 3-4 dependent L2/HBM round trips
-// (plan -> interval records -> point records -> values), ~2-3 us under load, while one SM's share of
-// HBM write bandwidth drains a 16 KB tile in ~0.37 us.  So >= 8 tiles must be in flight per SM:
-// 128-thread CTAs (4 warps, 16 interval groups) let 12 CTAs co-reside (17 KB smem, <= 64 regs).
+// Why (measured, profiles/r01): the first tile-per-CTA designs were issue-bound, ~2750 warp
+// instructions per 128 voxels, because 8-lane groups each re-derived indices for one interval.  Points
+// of a sub-tile are contiguous in the sorted rank arrays, so a warp loads 32 points' indices with one
+// coalesced instruction each and then walks them with lanes = channels (one 128-byte feature row per
+// point): ~230 instructions per sub-tile.
 // ----------------------------------------------------------------------------------------------
-constexpr int kTile         = 128;   // voxels per tile
-constexpr int kTileShift    = 7;
+constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
+constexpr int kSubShift     = 5;
 constexpr int kThreads      = 128;   // threads per CTA of the tile kernels
-constexpr int kGroupLanes   = 8;     // lanes cooperating on one interval: 8 x float4 = 32 channels/pass
-constexpr int kGroupsPerCta = kThreads / kGroupLanes;
-constexpr int kMaxChunks    = 4;     // channels <= 8 lanes * 4 floats * 4 chunks = 128 on the vector path
+constexpr int kWarpsPerCta  = kThreads / 32;
 
 // Forward-plan flags (device side, FwdPlanHeader::flags)
-constexpr int kFlagUnsorted   = 1;   // interval voxels not strictly increasing -> order-agnostic path
+constexpr int kFlagUnsorted   = 1;   // interval voxels not strictly increasing, or intervals not back to back in
+                                     // the point arrays -> order-agnostic path
 constexpr int kFlagOutOfRange = 2;   // some interval names a voxel / point range outside the tensors
 
 struct __align__(16) FwdPlanHeader {
     int32_t flags;
-    int32_t n_tiles;
-    int32_t tiles_per_sample;
+    int32_t n_subs;          // number of sub-tiles = B * subs_per_sample
+    int32_t subs_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
     int32_t structured;      // 1: pt2pos is valid (plan produced by fo_rank_prepare)
     int32_t reserved[11];
@@ -54,38 +56,40 @@ struct __align__(16) BwdPlanHeader {
 static_assert(sizeof(BwdPlanHeader) == 64, "header is one 64-byte block");
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline int64_t tiles_per_sample(int64_t n_vox) { return (n_vox + kTile - 1) / kTile; }
+__host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vox + kSub - 1) / kSub; }
 
 // ----------------------------------------------------------------------------------------------
 // Forward plan buffer:
-//   [header(256) | tile_off[tiles bound + 1] | pos2iv[P_cap] | pt2pos[P_cap] | iv_vox[IV_cap]]
-//   tile_off[t]   first interval whose voxel lies in tile t (tile_off[n_tiles] = n_intervals)
+//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | pos2iv[P_cap] | pt2pos[P_cap] | iv_vox[IV_cap]]
+//   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
+//   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
 //   pos2iv[i]     interval id of sorted position i (rows of the backward's gathered out_grad)
-//   iv_vox[k]     voxel id (= ranks_bev) of interval k: saves the ranks_bev[starts[k]] round trip
 //   pt2pos[p]     sorted position of frustum point p, -1 if filtered (only when hdr.structured)
+//   iv_vox[k]     voxel id (= ranks_bev) of interval k
 //   P_cap = point capacity rounded up to 64, IV_cap = min(P_cap, B*Z*Y*X rounded up to 64).
 // ----------------------------------------------------------------------------------------------
 struct FwdPlanView {
     FwdPlanHeader *hdr;
-    int32_t *tile_off;
+    int32_t *sub_iv;
+    int32_t *sub_pt;
     int32_t *pos2iv;
     int32_t *iv_vox;
     int32_t *pt2pos;
     int64_t p_cap;           // point capacity of this buffer (multiple of 64)
     int64_t iv_cap;          // interval capacity
 };
-__host__ inline int64_t fwd_plan_tiles_bound(int64_t n_vox_total) { return n_vox_total / kTile + 4096 + 1; }
-__host__ inline size_t fwd_plan_tile_bytes(int64_t n_vox_total) {
-    return (size_t)align_up((fwd_plan_tiles_bound(n_vox_total) + 1) * 4, 256);
+__host__ inline int64_t fwd_plan_subs_bound(int64_t n_vox_total) { return n_vox_total / kSub + 4096 + 1; }
+__host__ inline size_t fwd_plan_sub_bytes(int64_t n_vox_total) {
+    return (size_t)align_up((fwd_plan_subs_bound(n_vox_total) + 1) * 4, 256);
 }
 __host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
     const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
-    return 256 + fwd_plan_tile_bytes(n_vox_total) + (size_t)(8 * pc + 4 * (pc < nv ? pc : nv));
+    return 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(8 * pc + 4 * (pc < nv ? pc : nv));
 }
 // The layout is a pure function of (n_vox_total, plan_bytes): every entry point is handed the same
 // plan_bytes the buffer was sized with and recovers the same pointers without reading the device.
 __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_bytes, FwdPlanView *v) {
-    const size_t fixed = 256 + fwd_plan_tile_bytes(n_vox_total);
+    const size_t fixed = 256 + 2 * fwd_plan_sub_bytes(n_vox_total);
     if (plan_bytes < fixed + 64 * 12) return false;
     const int64_t rest = (int64_t)(plan_bytes - fixed), nv = align_up(n_vox_total, 64);
     int64_t pc = rest / 12;
@@ -93,7 +97,8 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
     pc = pc / 64 * 64;
     char *p = (char *)plan;
     v->hdr = (FwdPlanHeader *)p;             p += 256;
-    v->tile_off = (int32_t *)p;              p += fwd_plan_tile_bytes(n_vox_total);
+    v->sub_iv = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
+    v->sub_pt = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->pos2iv = (int32_t *)p;                p += pc * 4;
     v->pt2pos = (int32_t *)p;                p += pc * 4;
     v->iv_vox = (int32_t *)p;
@@ -174,7 +179,7 @@ int set_error(int code, const char *fmt, ...);
 
 // opens + validates a forward plan buffer (defined in rank_prepare.cu)
 int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
-                        FwdPlanView *pv, int64_t *n_tiles, int *tps);
+                        FwdPlanView *pv, int64_t *n_subs, int *sps);
 
 inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
     int64_t b = (work_items + per_block - 1) / per_block;
@@ -189,11 +194,12 @@ inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
 #ifdef __CUDACC__
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
-__device__ __forceinline__ void fma4(float4 &acc, const float4 &a, float b) {
-    acc.x = fmaf(a.x, b, acc.x);
-    acc.y = fmaf(a.y, b, acc.y);
-    acc.z = fmaf(a.z, b, acc.z);
-    acc.w = fmaf(a.w, b, acc.w);
+// Per-warp shared-memory stage of one sub-tile: channel-major [C][kSub] floats = the layout of the
+// (B,C,Z,Y,X) block itself, so it is drained / filled with LDS.128/STS.128 <-> 128-bit global
+// accesses.  The 16-byte chunk index inside a row is XOR-ed with (c & 7): a flush of one voxel's 32
+// channels (lane = channel) then spreads over 8 bank groups instead of hammering one bank.
+__device__ __forceinline__ int stage_index(int c, int v) {
+    return (c << kSubShift) + ((((v >> 2) ^ c) & 7) << 2) + (v & 3);
 }
 
 // streaming (evict-first) store: the dense voxel tensor is written once and not re-read here

@@ -24,7 +24,7 @@ struct VoxArgs {
     int32_t *key;                // [n_points] voxel id or -1 (lives in the plan: becomes pt2pos)
     int32_t *slot;               // [n_points]
     FwdPlanHeader *hdr;          // static fields initialised by thread 0
-    int32_t n_tiles, tiles_per_sample;
+    int32_t n_subs, subs_per_sample;
 };
 
 __device__ __forceinline__ int voxel_key(float x, float y, float z, int64_t b, const VoxArgs &a) {
@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid == 0) {
         a.hdr->flags = 0;
-        a.hdr->n_tiles = a.n_tiles;
-        a.hdr->tiles_per_sample = a.tiles_per_sample;
+        a.hdr->n_subs = a.n_subs;
+        a.hdr->subs_per_sample = a.subs_per_sample;
         a.hdr->structured = 1;
     }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -101,11 +101,11 @@ __global__ void __launch_bounds__(256) place_kernel(const int32_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Forward plan from caller-supplied interval arrays (fo_fwd_plan_build).
 // ------------------------------------------------------------------------------------------------
-__global__ void init_fwd_header_kernel(FwdPlanHeader *hdr, int n_tiles, int tps, int n_intervals) {
+__global__ void init_fwd_header_kernel(FwdPlanHeader *hdr, int n_subs, int sps, int n_intervals) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         hdr->flags = 0;
-        hdr->n_tiles = n_tiles;
-        hdr->tiles_per_sample = tps;
+        hdr->n_subs = n_subs;
+        hdr->subs_per_sample = sps;
         hdr->n_intervals = n_intervals;
         hdr->structured = 0;
     }
@@ -122,14 +122,14 @@ __device__ __forceinline__ int interval_voxel(const int32_t *rb, const int32_t *
 __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
     const int32_t *__restrict__ rb, const int32_t *__restrict__ starts, const int32_t *__restrict__ lengths,
     int64_t n_points, int64_t n_cap, const int32_t *__restrict__ n_dev, int64_t vox_per_sample,
-    int64_t n_vox_total, int tps, int n_tiles, FwdPlanHeader *hdr, int32_t *tile_off, int32_t *pos2iv,
-    int32_t *iv_vox) {
+    int64_t n_vox_total, int sps, int n_subs, FwdPlanHeader *hdr, int32_t *sub_iv, int32_t *sub_pt,
+    int32_t *pos2iv, int32_t *iv_vox) {
     const int64_t n = n_dev ? min((int64_t)max(*n_dev, 0), n_cap) : n_cap;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid == 0) hdr->n_intervals = (int)n;
     if (n == 0) {
-        for (int64_t t = gtid; t <= n_tiles; t += stride) tile_off[t] = 0;
+        for (int64_t t = gtid; t <= n_subs; t += stride) { sub_iv[t] = 0; sub_pt[t] = 0; }
         return;
     }
     for (int64_t k = gtid; k < n; k += stride) {
@@ -142,15 +142,19 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
         }
         const int s = starts[k], len = lengths[k];
         for (int j = 0; j < len; ++j) pos2iv[s + j] = (int)k;
-        if (k > 0 && (vp < 0 || v <= vp)) {   // vp < 0: interval k-1 is invalid, its own thread raised the flags
+        // fast path needs: strictly increasing voxels, intervals back to back, every point of an interval
+        // carrying the interval's voxel (then runs of equal ranks_bev == intervals)
+        bool clean = len >= 1 && !(k > 0 && (vp < 0 || v <= vp || starts[k - 1] + lengths[k - 1] != s));
+        for (int j = 1; j < len && clean; ++j) clean = rb[s + j] == v;
+        if (!clean) {
             atomicOr(&hdr->flags, kFlagUnsorted);
             continue;
         }
-        const int64_t t = (v / vox_per_sample) * tps + (v % vox_per_sample) / kTile;
-        const int64_t tp = (k > 0) ? ((vp / vox_per_sample) * tps + (vp % vox_per_sample) / kTile) : -1;
-        for (int64_t u = tp + 1; u <= t; ++u) tile_off[u] = (int)k;
+        const int64_t u = (v / vox_per_sample) * sps + ((v % vox_per_sample) >> kSubShift);
+        const int64_t up = (k > 0) ? ((vp / vox_per_sample) * sps + ((vp % vox_per_sample) >> kSubShift)) : -1;
+        for (int64_t t = up + 1; t <= u; ++t) { sub_iv[t] = (int)k; sub_pt[t] = s; }
         if (k == n - 1)
-            for (int64_t u = t + 1; u <= n_tiles; ++u) tile_off[u] = (int)n;
+            for (int64_t t = u + 1; t <= n_subs; ++t) { sub_iv[t] = (int)n; sub_pt[t] = s + len; }
     }
 }
 
@@ -244,7 +248,7 @@ extern "C" size_t fo_fwd_plan_bytes(int64_t n_voxels_total, int64_t n_points_cap
 namespace {
 // shared checks for entry points that take a forward plan
 int open_fwd_plan(void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points, FwdPlanView *pv,
-                  int64_t *n_tiles, int *tps) {
+                  int64_t *n_subs, int *sps) {
     FO_CHECK_ARG(plan != nullptr, "forward plan is NULL");
     FO_CHECK_ARG(B >= 1 && n_vox >= 1, "B=%d and n_voxels_per_sample=%lld must be positive", B, (long long)n_vox);
     FO_CHECK_ARG((int64_t)B * n_vox < INT_MAX, "B*Z*Y*X = %lld does not fit int32 ranks", (long long)B * n_vox);
@@ -253,15 +257,15 @@ int open_fwd_plan(void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64
     if (!fwd_plan_view(plan, (int64_t)B * n_vox, plan_bytes, pv) || pv->p_cap < n_points)
         return set_error(FO_ERR_SCRATCH, "forward plan buffer is %zu bytes, need %zu for %lld points", plan_bytes,
                          fwd_plan_bytes_for((int64_t)B * n_vox, n_points), (long long)n_points);
-    *tps = (int)tiles_per_sample(n_vox);
-    *n_tiles = (int64_t)(*tps) * B;
+    *sps = (int)subs_per_sample(n_vox);
+    *n_subs = (int64_t)(*sps) * B;
     return FO_OK;
 }
 
 struct SortScratch {
     int32_t *cnt;
-    unsigned long long *state;
-    int32_t *counter;
+    unsigned long long *agg;     // per-scan-tile (points << 32 | non-empty buckets)
+    int32_t *counter;            // long-interval queue length
     size_t zero_bytes;
 };
 SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
@@ -269,7 +273,7 @@ SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     SortScratch s;
     char *p = (char *)base;
     s.cnt = (int32_t *)p;                       p += align_up(n_buckets * 4, 256);
-    s.state = (unsigned long long *)p;          p += align_up(n_scan_tiles * 8, 256);
+    s.agg = (unsigned long long *)p;            p += align_up(n_scan_tiles * 8, 256);
     s.counter = (int32_t *)p;                   p += 256;
     s.zero_bytes = (size_t)(p - (char *)base);
     return s;
@@ -280,8 +284,8 @@ static_assert(kScanTile == 4096, "bucket_zero_bytes() in common.cuh assumes 4096
 // exported for the other translation units
 namespace fo {
 int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
-                        FwdPlanView *pv, int64_t *n_tiles, int *tps) {
-    return open_fwd_plan(const_cast<void *>(plan), plan_bytes, B, n_vox, n_points, pv, n_tiles, tps);
+                        FwdPlanView *pv, int64_t *n_subs, int *sps) {
+    return open_fwd_plan(const_cast<void *>(plan), plan_bytes, B, n_vox, n_points, pv, n_subs, sps);
 }
 }  // namespace fo
 
@@ -292,16 +296,16 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
     cudaStream_t stream = (cudaStream_t)stream_;
     FO_CHECK_ARG(n_points >= 0 && n_intervals >= 0 && n_points < INT_MAX, "negative or oversized counts");
     FO_CHECK_ARG(n_intervals == 0 || (ranks_bev && interval_starts && interval_lengths), "NULL index array");
-    FwdPlanView pv; int64_t n_tiles; int tps;
-    if (int rc = open_fwd_plan(plan, plan_bytes, B, n_vox, n_points, &pv, &n_tiles, &tps)) return rc;
+    FwdPlanView pv; int64_t n_subs; int sps;
+    if (int rc = open_fwd_plan(plan, plan_bytes, B, n_vox, n_points, &pv, &n_subs, &sps)) return rc;
     FO_CHECK_ARG(n_intervals <= pv.iv_cap, "n_intervals=%lld exceeds the plan's interval capacity %lld",
                  (long long)n_intervals, (long long)pv.iv_cap);
-    init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_tiles, tps, (int)n_intervals);
+    init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_subs, sps, (int)n_intervals);
     FO_LAUNCH_CHECK("init_fwd_header_kernel");
-    const int64_t work = n_intervals > n_tiles + 1 ? n_intervals : n_tiles + 1;
+    const int64_t work = n_intervals > n_subs + 1 ? n_intervals : n_subs + 1;
     plan_from_intervals_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
         ranks_bev, interval_starts, interval_lengths, n_points, n_intervals, n_intervals_dev, n_vox,
-        (int64_t)B * n_vox, tps, (int)n_tiles, pv.hdr, pv.tile_off, pv.pos2iv, pv.iv_vox);
+        (int64_t)B * n_vox, sps, (int)n_subs, pv.hdr, pv.sub_iv, pv.sub_pt, pv.pos2iv, pv.iv_vox);
     FO_LAUNCH_CHECK("plan_from_intervals_kernel");
     return FO_OK;
 }
@@ -333,8 +337,8 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     const size_t need = fo_rank_prepare_scratch_bytes(P, NV);
     if (scratch_bytes < need)
         return set_error(FO_ERR_SCRATCH, "rank scratch is %zu bytes, need %zu", scratch_bytes, need);
-    FwdPlanView pv; int64_t n_tiles; int tps;
-    if (int rc = open_fwd_plan(fwd_plan, fwd_plan_bytes, B, n_vox, P, &pv, &n_tiles, &tps)) return rc;
+    FwdPlanView pv; int64_t n_subs; int sps;
+    if (int rc = open_fwd_plan(fwd_plan, fwd_plan_bytes, B, n_vox, P, &pv, &n_subs, &sps)) return rc;
 
     SortScratch ss = sort_scratch_view(scratch, NV);
     int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
@@ -349,7 +353,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     va.ivx = interval[0]; va.ivy = interval[1]; va.ivz = interval[2];
     va.X = X; va.Y = Y; va.Z = Z;
     va.cnt = ss.cnt; va.key = key; va.slot = slot;
-    va.hdr = pv.hdr; va.n_tiles = (int)n_tiles; va.tiles_per_sample = tps;
+    va.hdr = pv.hdr; va.n_subs = (int)n_subs; va.subs_per_sample = sps;
     voxelize_count_kernel<<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va);
     FO_LAUNCH_CHECK("voxelize_count_kernel");
 
@@ -357,10 +361,13 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     sa.cnt = ss.cnt; sa.n_buckets = NV;
     sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = pv.iv_vox;
     sa.totals = counts_dev;
-    sa.tile_off = pv.tile_off; sa.vox_per_sample = n_vox; sa.tiles_per_sample = tps; sa.n_tiles = (int)n_tiles;
+    sa.sub_iv = pv.sub_iv; sa.sub_pt = pv.sub_pt; sa.vox_per_sample = n_vox; sa.subs_per_sample = sps;
+    sa.n_subs = (int)n_subs;
     sa.fwd_hdr = pv.hdr; sa.bwd_hdr = nullptr;
-    sa.state = ss.state; sa.tile_counter = ss.counter;
+    sa.agg = ss.agg;
     const int scan_blocks = (int)((NV + kScanTile - 1) / kScanTile);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, NV, ss.agg);
+    FO_LAUNCH_CHECK("tile_reduce_kernel");
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
 
@@ -372,9 +379,12 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev; oa.pos2iv = pv.pos2iv; oa.pt2pos = pv.pt2pos;
     oa.dhw = D * H * W; oa.hw = H * W;
+    oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     const int64_t cap_iv = P < NV ? P : NV;
-    order_segments_kernel<true><<<grid_for(cap_iv, kSortThreads, 16), kSortThreads, 0, stream>>>(oa);
-    FO_LAUNCH_CHECK("order_segments_kernel<fwd>");
+    order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_short_kernel<fwd>");
+    order_long_kernel<true><<<148 * 4, kSortThreads, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_long_kernel<fwd>");
     return FO_OK;
 }
 
@@ -391,8 +401,8 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     FO_CHECK_ARG(plan != nullptr && ((uintptr_t)plan & 255) == 0, "backward plan must be non-NULL, 256-byte aligned");
     FO_CHECK_ARG(n_points >= 0 && n_points < INT_MAX && n_feat_rows >= 1 && n_feat_rows < INT_MAX && n_depth >= 0,
                  "bad sizes n_points=%lld n_feat_rows=%lld", (long long)n_points, (long long)n_feat_rows);
-    FwdPlanView fv; int64_t n_tiles; int tps;
-    if (int rc = open_fwd_plan_const(fwd_plan, fwd_plan_bytes, B, n_vox, n_points, &fv, &n_tiles, &tps)) return rc;
+    FwdPlanView fv; int64_t n_subs; int sps;
+    if (int rc = open_fwd_plan_const(fwd_plan, fwd_plan_bytes, B, n_vox, n_points, &fv, &n_subs, &sps)) return rc;
     BwdPlanView bv;
     const bool structured = (flags & FO_BWD_PLAN_STRUCTURED) != 0;
     const int64_t need_cap = structured ? n_depth : n_points;
@@ -439,10 +449,12 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     sa.cnt = ss.cnt; sa.n_buckets = n_feat_rows;
     sa.iv_starts = bv.starts; sa.iv_lengths = bv.lengths; sa.iv_bucket = bv.ids;
     sa.totals = bv.hdr->totals;
-    sa.tile_off = nullptr; sa.vox_per_sample = 1; sa.tiles_per_sample = 0; sa.n_tiles = 0;
+    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = bv.hdr;
-    sa.state = ss.state; sa.tile_counter = ss.counter;
+    sa.agg = ss.agg;
     const int scan_blocks = (int)((n_feat_rows + kScanTile - 1) / kScanTile);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_feat_rows, ss.agg);
+    FO_LAUNCH_CHECK("tile_reduce_kernel");
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
     place_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(ranks_feat, bv.slot, ss.cnt, n_points, n_points_dev,
@@ -452,8 +464,11 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
     oa.n_intervals = &bv.hdr->n_bwd_intervals;
     oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.pos2iv = nullptr; oa.pt2pos = nullptr; oa.dhw = 1; oa.hw = 1;
-    order_segments_kernel<false><<<grid_for(n_feat_rows, kSortThreads, 16), kSortThreads, 0, stream>>>(oa);
-    FO_LAUNCH_CHECK("order_segments_kernel<bwd>");
+    oa.long_list = bv.slot; oa.long_count = ss.counter;
+    order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_short_kernel<bwd>");
+    order_long_kernel<false><<<148 * 4, kSortThreads, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_long_kernel<bwd>");
     bwd_plan_fill_entries_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(bv.pos, ranks_depth, fv.pos2iv, bv.hdr,
                                                                               bv.cap, bv.ent_p, bv.ent_iv);
     FO_LAUNCH_CHECK("bwd_plan_fill_entries_kernel");
