@@ -34,27 +34,41 @@ struct FwdArgs {
     const int32_t *sub_pt;
 };
 
-constexpr int kFwdUnroll = 4;       // feature rows in flight per lane
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_zero4(unsigned addr) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 // NACC = ceil(C / 32) accumulators per lane; EXACT: C == 32 * NACC (no channel predicates).
 //
-// Instruction budget (the first versions of this kernel were ISSUE-bound, ~800 warp instructions per
-// sub-tile, profiles/r01): point records are broadcast through a per-warp shared-memory array (one
-// LDS.64 per point: no shuffles, hence no WARPSYNC sequences in the loop), feature-row addresses are
-// 32-bit, four rows are in flight per lane, and all index arithmetic is 32-bit.
+// Two things bound the first versions of this kernel (profiles/r01): instruction issue (~700 warp
+// instructions per sub-tile) and the few dense near-ego sub-tiles (up to 844 points at the headline
+// shape, 3 394 at 512x1408) whose strictly sequential FMA chain exposed one L2 round trip per four
+// points.  Hence: point records are broadcast through a per-warp shared-memory array (LDS.128 = two
+// records, no shuffles), shared-memory addresses are precomputed 32-bit values, feature rows are
+// fetched in groups of U with the NEXT group already in flight while the current one is consumed
+// (2*U rows in flight per lane), and the next 32 records are fetched while a batch is processed.
 template <int NACC, bool EXACT, int LAYOUT>
 __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
+    constexpr int U = NACC <= 2 ? 8 : 4;                 // feature rows per group
     extern __shared__ __align__(16) float smem[];
-    __shared__ int2 s_rec[kWarpsPerCta][32 + kFwdUnroll];
+    __shared__ __align__(16) int2 s_rec[kWarpsPerCta][32 + 8];
     if (a.hdr->flags & kFlagUnsorted) return;            // the order-agnostic path runs instead
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = EXACT ? 32 * NACC : a.C;
-    // CTA i -> sample i % B, four consecutive sub-tiles: the dense (near-ego) regions of all samples
-    // are reached at the same relative time instead of the last sample's trailing the whole grid
+    // grid = (B, ceil(subs_per_sample / 4)): x-fastest block order interleaves the samples, so the dense
+    // near-ego regions of all samples are reached at the same relative time
     const int sps = a.hdr->subs_per_sample;
-    const int b = blockIdx.x % a.B;
-    const int su = (blockIdx.x / a.B) * kWarpsPerCta + warp;
+    const int b = blockIdx.x;
+    const int su = blockIdx.y * kWarpsPerCta + warp;
     if (su >= sps) return;
     const int u = b * sps + su;
     const int v0 = su << kSubShift;
@@ -62,87 +76,119 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
     const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
     const int vbase = (int)((int64_t)b * a.V) + v0;      // global voxel id of the sub-tile's first voxel (< 2^31)
     const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((a.V & 3) == 0);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float *plane0 = a.out + ((int64_t)b * C) * a.V + v0;
-    const int row_in_quad = lane >> 3, chunk = lane & 7;
+    const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
 
     if (pa >= pb && vec_out) {                            // empty sub-tile: stream zeros, no staging
         if (4 * chunk < nv) {
-            float *dst = plane0 + (int64_t)row_in_quad * a.V + 4 * chunk;
+            float *dst = plane0 + (int64_t)riq * a.V + 4 * chunk;
             const int64_t step = 4 * a.V;
-            for (int r = row_in_quad; r < C; r += 4, dst += step) __stcs(reinterpret_cast<float4 *>(dst), zero4);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = riq; r < C; r += 4, dst += step) __stcs(reinterpret_cast<float4 *>(dst), zero4);
         }
         return;
     }
     float *stage = smem + warp * C * kSub;
-    float4 *stage4 = reinterpret_cast<float4 *>(stage);
-    for (int e = lane; e < C * (kSub / 4); e += 32) stage4[e] = zero4;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+    for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
     int2 *rec = s_rec[warp];
-    if (lane < kFwdUnroll) rec[32 + lane] = make_int2(0, 0);
+    const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
 
-    float acc[NACC];
-#pragma unroll
-    for (int r = 0; r < NACC; ++r) acc[r] = 0.f;
-    int cur_v = -1;
-    for (int i0 = pa; i0 < pb; i0 += 32) {
-        const int n = min(32, pb - i0);
-        int2 mine = make_int2(0, 0);                      // (feature row << 5 | voxel in sub-tile, depth bits)
-        if (lane < n) {
+    auto load_rec = [&](int i0) -> int2 {
+        int2 m = make_int2(0, 0);                         // (feature row << 5 | voxel in sub-tile, depth bits)
+        if (i0 + lane < pb) {
             const int q = __ldg(a.rf + i0 + lane);
             const int v = __ldg(a.rb + i0 + lane) - vbase;
-            mine.x = (q << kSubShift) | (v & (kSub - 1));
-            mine.y = __float_as_int(__ldg(a.depth + __ldg(a.rd + i0 + lane)));
+            m.x = (q << kSubShift) | (v & (kSub - 1));
+            m.y = __float_as_int(__ldg(a.depth + __ldg(a.rd + i0 + lane)));
         }
+        return m;
+    };
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    int cur_v = -1;
+    auto flush = [&]() {
+        const unsigned off = ((((unsigned)(cur_v >> 2) ^ (unsigned)lane) & 7u) << 4) + (((unsigned)cur_v & 3u) << 2);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+            if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
+    };
+    auto load_group = [&](float (&f)[U][NACC], int j) {
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+            const int row = (rec[j + t].x >> kSubShift) * C + lane;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
+        }
+    };
+    auto consume = [&](const float (&f)[U][NACC], int j, int count) {
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+            if (t < count) {                              // warp-uniform
+                const int2 r = rec[j + t];
+                const int v = r.x & (kSub - 1);
+                if (v != cur_v) {                         // warp-uniform: a new interval starts
+                    if (cur_v >= 0) flush();
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+                    cur_v = v;
+                }
+                const float d = __int_as_float(r.y);
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d, acc[k]);
+            }
+        }
+    };
+
+    int2 mine = load_rec(pa);
+    for (int i0 = pa; i0 < pb; i0 += 32) {
+        const int n = min(32, pb - i0);
         __syncwarp();
         rec[lane] = mine;
+        if (lane < 8) rec[32 + lane] = make_int2(0, 0);
         __syncwarp();
-        for (int j = 0; j < n; j += kFwdUnroll) {
-            int2 r[kFwdUnroll];
-            float f[kFwdUnroll][NACC];
-#pragma unroll
-            for (int t = 0; t < kFwdUnroll; ++t) r[t] = rec[j + t];
-#pragma unroll
-            for (int t = 0; t < kFwdUnroll; ++t) {
-                const int row = (r[t].x >> kSubShift) * C + lane;
-#pragma unroll
-                for (int k = 0; k < NACC; ++k)
-                    f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
-            }
-#pragma unroll
-            for (int t = 0; t < kFwdUnroll; ++t) {
-                if (j + t < n) {                          // warp-uniform
-                    const int v = r[t].x & (kSub - 1);
-                    if (v != cur_v) {                     // warp-uniform: a new interval starts
-                        if (cur_v >= 0) {
-#pragma unroll
-                            for (int k = 0; k < NACC; ++k)
-                                if (EXACT || lane + 32 * k < C) stage[stage_index(lane + 32 * k, cur_v)] = acc[k];
-                        }
-#pragma unroll
-                        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-                        cur_v = v;
-                    }
-                    const float d = __int_as_float(r[t].y);
-#pragma unroll
-                    for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d, acc[k]);
+        if (i0 + 32 < pb) mine = load_rec(i0 + 32);       // next batch's records fly during this batch
+        const int nfull = n & ~(U - 1);
+        float fa[U][NACC], fb[U][NACC];
+        if (nfull) {
+            load_group(fa, 0);
+            for (int j = 0; j < nfull; j += 2 * U) {
+                const bool has_b = j + U < nfull;
+                if (has_b) load_group(fb, j + U);
+                consume(fa, j, U);
+                if (has_b) {
+                    if (j + 2 * U < nfull) load_group(fa, j + 2 * U);
+                    consume(fb, j + U, U);
                 }
             }
         }
+        if (nfull < n) {                                  // remainder group: rows of padding records are row 0
+            load_group(fa, nfull);
+            consume(fa, nfull, n - nfull);
+        }
     }
-    if (cur_v >= 0) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k)
-            if (EXACT || lane + 32 * k < C) stage[stage_index(lane + 32 * k, cur_v)] = acc[k];
-    }
+    if (cur_v >= 0) flush();
     __syncwarp();
 
     if (LAYOUT == FO_LAYOUT_BCZYX) {
         if (vec_out) {
-            // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction
-            for (int r = row_in_quad; r < C; r += 4) {
-                const int ck = (chunk ^ r) & 7;                       // logical chunk stored at position `chunk`
-                if (4 * ck < nv)
-                    __stcs(reinterpret_cast<float4 *>(plane0 + (int64_t)r * a.V + 4 * ck), stage4[r * (kSub / 4) + chunk]);
+            // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
+            // logical chunk stored at smem position `chunk` of row r is (chunk ^ r) & 7: it alternates
+            // between two values as r advances by 4.
+            const int ck0 = (chunk ^ riq) & 7, ck1 = ck0 ^ 4;
+            float *d0 = plane0 + (int64_t)riq * a.V + 4 * ck0;
+            float *d1 = plane0 + (int64_t)(riq + 4) * a.V + 4 * ck1;
+            const int64_t step = 8 * a.V;
+            unsigned sa = sbase + ((unsigned)riq << 7) + ((unsigned)chunk << 4);
+            const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
+            for (int r = riq; r < C; r += 8, d0 += step, d1 += step, sa += 1024u) {
+                const float4 x0 = lds_f4(sa);
+                if (w0) __stcs(reinterpret_cast<float4 *>(d0), x0);
+                if (r + 4 < C) {
+                    const float4 x1 = lds_f4(sa + 512u);
+                    if (w1) __stcs(reinterpret_cast<float4 *>(d1), x1);
+                }
             }
         } else {
             for (int e = lane; e < C * kSub; e += 32) {
@@ -210,7 +256,7 @@ template <int NACC, bool EXACT, int LAYOUT>
 int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_ctas, kThreads, smem, stream>>>(a);
+    kern<<<dim3(a.B, n_ctas), kThreads, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
     return FO_OK;
 }
@@ -264,10 +310,9 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
 
     const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
     // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
-    const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_points < (1 << 26) &&
-                          (int64_t)B * n_vox * 1 < INT_MAX;
+    const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;      // per sample (grid.y)
+    const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas <= 65535 && B <= 65535;
     if (dense_ok) {
-        const int n_ctas = (int)(((int64_t)sps + kWarpsPerCta - 1) / kWarpsPerCta) * B;
         int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
                                                  : launch_dense_any<FO_LAYOUT_BZYXC>(a, n_ctas, smem, stream);
         if (rc) return rc;
