@@ -27,61 +27,85 @@ struct GatherArgs {
     float *G;                       // [n_intervals, C]
 };
 
-// One warp per 32-voxel sub-tile (same tiling as the forward).  The C x 32 block of out_grad is read
-// with 128-bit loads, four full 128-byte lines per instruction, a 16-byte chunk being fetched only if
-// one of its four voxels is occupied (untouched sectors never leave HBM); it is staged in the
-// swizzled channel-major layout and one compact channels-last row G[k, 0..C) is emitted per interval.
+__device__ __forceinline__ void sts_f4(unsigned addr, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// One warp per 32-voxel sub-tile (same tiling and grid as the forward).  The C x 32 block of out_grad
+// is read with 128-bit loads, four full 128-byte lines per instruction, a 16-byte chunk being fetched
+// only if one of its four voxels is occupied; it is staged in the swizzled channel-major layout and one
+// compact channels-last row G[k, 0..C) is emitted per interval.
 __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = a.C;
-    const int64_t u = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    if (u >= a.hdr->n_subs) return;
+    const int sps = a.hdr->subs_per_sample;
+    const int b = blockIdx.x;
+    const int su = blockIdx.y * kWarpsPerCta + warp;
+    if (su >= sps) return;
+    const int u = b * sps + su;
     const int ia = __ldg(a.sub_iv + u), ib = __ldg(a.sub_iv + u + 1);
     if (ib <= ia) return;
-    const int sps = a.hdr->subs_per_sample;
-    const int b = (int)(u / sps);
-    const int64_t v0 = (u - (int64_t)b * sps) << kSubShift;
+    const int v0 = su << kSubShift;
     const int nv = (int)min((int64_t)kSub, a.V - v0);
-    const int64_t vbase = (int64_t)b * a.V + v0;
+    const int vbase = (int)((int64_t)b * a.V) + v0;
     const int ni = min(ib - ia, kSub);
-    float *stage = smem + (size_t)warp * C * kSub;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem + warp * C * kSub);
 
     int my_v = -1;
     if (lane < ni) {
-        my_v = (int)(__ldg(a.iv_vox + ia + lane) - vbase);
+        my_v = __ldg(a.iv_vox + ia + lane) - vbase;
         if ((unsigned)my_v >= (unsigned)nv) my_v = -1;
     }
     const unsigned occ = __reduce_or_sync(0xffffffffu, my_v >= 0 ? (1u << my_v) : 0u);
     const float *plane0 = a.og + ((int64_t)b * C) * a.V + v0;
     if ((a.V & 3) == 0) {
-        const int row_in_quad = lane >> 3, chunk = lane & 7;
-        const bool want = ((occ >> (4 * chunk)) & 0xFu) != 0u;
-        float4 *stage4 = reinterpret_cast<float4 *>(stage);
-        for (int r0 = row_in_quad; r0 < C; r0 += 16) {
-            float4 v[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int r = r0 + 4 * t;
-                v[t] = (want && r < C) ? __ldcs(reinterpret_cast<const float4 *>(plane0 + (int64_t)r * a.V) + chunk)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int riq = lane >> 3, chunk = lane & 7;
+        if (((occ >> (4 * chunk)) & 0xFu) != 0u) {
+            const float *src = plane0 + (int64_t)riq * a.V + 4 * chunk;
+            const int64_t step = 4 * a.V;
+            // smem position of logical chunk `chunk` in row r is (chunk ^ r) & 7: two alternating values
+            const unsigned s0 = sbase + ((unsigned)riq << 7) + ((unsigned)((chunk ^ riq) & 7) << 4);
+            const unsigned s1 = sbase + ((unsigned)(riq + 4) << 7) + ((unsigned)((chunk ^ riq ^ 4) & 7) << 4);
+            int r = riq;
+            for (; r + 12 < C; r += 16, src += 4 * step) {
+                const float4 x0 = __ldcs(reinterpret_cast<const float4 *>(src));
+                const float4 x1 = __ldcs(reinterpret_cast<const float4 *>(src + step));
+                const float4 x2 = __ldcs(reinterpret_cast<const float4 *>(src + 2 * step));
+                const float4 x3 = __ldcs(reinterpret_cast<const float4 *>(src + 3 * step));
+                const unsigned o = (unsigned)(r - riq) << 7;
+                sts_f4(s0 + o, x0); sts_f4(s1 + o, x1); sts_f4(s0 + o + 1024u, x2); sts_f4(s1 + o + 1024u, x3);
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int r = r0 + 4 * t;
-                if (want && r < C) stage4[r * (kSub / 4) + ((chunk ^ r) & 7)] = v[t];
+            for (; r < C; r += 4, src += step) {
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(src));
+                sts_f4(sbase + ((unsigned)r << 7) + ((unsigned)((chunk ^ r) & 7) << 4), x);
             }
         }
     } else {
-        for (int c = 0; c < C; ++c)
-            if ((occ >> lane) & 1u) stage[stage_index(c, lane)] = __ldcs(plane0 + (int64_t)c * a.V + lane);
+        if ((occ >> lane) & 1u)
+            for (int c = 0; c < C; ++c)
+                sts_f32(sbase + 4u * stage_index(c, lane), __ldcs(plane0 + (int64_t)c * a.V + lane));
     }
     __syncwarp();
-    for (int l = 0; l < ni; ++l) {
+    float *dst = a.G + (int64_t)ia * C + lane;
+    for (int l = 0; l < ni; ++l, dst += C) {
         const int v = __shfl_sync(0xffffffffu, my_v, l);
         if (v < 0) continue;
-        float *dst = a.G + (int64_t)(ia + l) * C;
-        for (int c = lane; c < C; c += 32) dst[c] = stage[stage_index(c, v)];
+        const unsigned off = ((unsigned)lane << 7) + ((((unsigned)(v >> 2) ^ (unsigned)lane) & 7u) << 4) + (((unsigned)v & 3u) << 2);
+        for (int c = lane, k = 0; c < C; c += 32, ++k) dst[32 * k] = lds_f32(sbase + off + 4096u * k);
     }
 }
 
@@ -105,91 +129,109 @@ constexpr int kPixWarps   = kPixThreads / 32;
 constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 
 // One WARP per backward interval (= image pixel), points taken 32 at a time in the plan's order.
-//   stage   lane j fetches entry j (depth index, interval id) and its depth value; the 32 gathered
-//           out_grad rows are loaded four per instruction (8 lanes x float4 = one 128-byte row) into a
-//           per-warp shared-memory tile rows[32][C+4] (row stride C+4 keeps LDS.128 conflict-free).
+//   records lane j fetches entry j (depth index, G row) and its depth value; they are broadcast through
+//           shared memory (LDS.128 = two records); the next pass's records are fetched during this pass.
+//   rows    lanes = channels: each point's gathered out_grad row is one coalesced 128-byte load, eight
+//           rows in flight; the row goes (a) straight into feat_grad[q][c] += row[c] * depth[p] — the
+//           sequential FMA over the pixel's points in plan order (bev_pool_cuda.cu:109-120), accumulators
+//           in registers across passes — and (b) into the per-warp tile rows[32][C+4].
 //   depth   lane j owns point j: depth_grad[p_j] = sum_c rows[j][c] * feat[q][c] as ONE sequential FMA
-//           chain over c = 0..C-1 in one thread (bev_pool_cuda.cu:96-101) — 2 LDS.128 + 4 FFMA per 4
-//           channels for 32 points at once.
-//   feat    lane c owns channel c (+32, +64 ...): feat_grad[q][c] = sum_j rows[j][c] * depth[p_j]
-//           sequentially over the pixel's points (bev_pool_cuda.cu:109-120); accumulators stay in
-//           registers across passes, so the order is exact for any number of points.
+//           chain over c = 0..C-1 in one thread (bev_pool_cuda.cu:96-101): 2 LDS.128 + 4 FFMA per four
+//           channels for 32 points at once (row stride C+4 keeps the LDS.128 conflict-free).
 // NACC = ceil(C / 32) feat accumulators per lane.  Vector path: C % 4 == 0.
 template <int NACC>
 __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
+    constexpr int U = NACC <= 2 ? 8 : 4;
     extern __shared__ __align__(16) float psm[];
+    __shared__ __align__(16) int2 s_rec[kPixWarps][kPixChunk + 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = a.C, c4 = C >> 2, S = C + 4;
-    float *rows = psm + (size_t)warp * (kPixChunk * S + C + kPixChunk);    // [32][S]
-    float *fs = rows + kPixChunk * S;                                       // feat row of the pixel [C]
-    float *ds = fs + C;                                                     // depth values of the pass [32]
+    float *rows = psm + (size_t)warp * (kPixChunk * S + C);                 // [32][S]
+    float *fs = rows + kPixChunk * S;                                        // feat row of the pixel [C]
+    const unsigned rows_s = (unsigned)__cvta_generic_to_shared(rows);
+    const unsigned fs_s = (unsigned)__cvta_generic_to_shared(fs);
+    int2 *rec = s_rec[warp];
     const int64_t n = a.n_bwd_dev ? min((int64_t)max(*a.n_bwd_dev, 0), a.n_bwd) : a.n_bwd;
     const int64_t warp0 = (int64_t)blockIdx.x * kPixWarps + warp;
     const int64_t nwarps = (int64_t)gridDim.x * kPixWarps;
-    const int sub = lane >> 3, gl = lane & 7;          // row-in-quad, 16-byte column group
 
     for (int64_t m = warp0; m < n; m += nwarps) {
         const int s = __ldg(a.bwd_starts + m), len = __ldg(a.bwd_lengths + m);
         const int q = __ldg(a.bwd_ids + m);
         if (len <= 0 || s < 0 || (int64_t)s + len > a.n_entries || q < 0 || q >= a.n_feat_rows) continue;
+        auto load_rec = [&](int j0, int &p_out) -> int2 {
+            int2 r = make_int2(-1, 0);                    // (G row or -1, depth bits)
+            p_out = -1;
+            if (j0 + lane < len) {
+                int p = __ldg(a.ent_p + s + j0 + lane);
+                int row = __ldg(a.ent_iv + s + j0 + lane);
+                if (a.row_map) row = (row >= 0 && row < a.n_iv) ? __ldg(a.row_map + row) : -1;
+                if (p >= 0 && p < a.n_depth && row >= 0 && row < a.n_rows_G) {
+                    r.x = row;
+                    r.y = __float_as_int(__ldg(a.depth + p));
+                    p_out = p;
+                }
+            }
+            return r;
+        };
+        int my_p;
+        int2 mine = load_rec(0, my_p);
         __syncwarp();
         for (int i = lane; i < c4; i += 32)
             reinterpret_cast<float4 *>(fs)[i] = ldg4(a.feat + ((int64_t)q * c4 + i) * 4);
         float fg[NACC];
 #pragma unroll
-        for (int r = 0; r < NACC; ++r) fg[r] = 0.f;
+        for (int k = 0; k < NACC; ++k) fg[k] = 0.f;
 
         for (int j0 = 0; j0 < len; j0 += kPixChunk) {
             const int np = min(kPixChunk, len - j0);
-            int my_p = -1, my_row = -1;
-            if (lane < np) {
-                my_p = __ldg(a.ent_p + s + j0 + lane);
-                const int iv = __ldg(a.ent_iv + s + j0 + lane);
-                my_row = iv;
-                if (a.row_map) my_row = (iv >= 0 && iv < a.n_iv) ? __ldg(a.row_map + iv) : -1;
-                if (my_p < 0 || my_p >= a.n_depth || my_row < 0 || my_row >= a.n_rows_G) { my_p = -1; my_row = -1; }
-            }
-            const float my_d = (my_p >= 0) ? __ldg(a.depth + my_p) : 0.f;
-            __syncwarp();                               // previous pass finished reading rows / ds
-            ds[lane] = my_d;
-            // gather: 4 rows per instruction
-            for (int r0 = 0; r0 < np; r0 += 4) {
-                const int row = __shfl_sync(0xffffffffu, my_row, r0 + sub);
-                for (int i = gl; i < c4; i += 8) {
-                    const float4 v = (row >= 0) ? ldg4(a.G + ((int64_t)row * c4 + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4 *>(rows + (r0 + sub) * S + 4 * i) = v;
+            const int cur_p = my_p;
+            __syncwarp();                               // previous pass finished reading rows / rec
+            rec[lane] = mine;
+            if (lane < 8) rec[kPixChunk + lane] = make_int2(-1, 0);
+            __syncwarp();
+            if (j0 + kPixChunk < len) mine = load_rec(j0 + kPixChunk, my_p);
+            for (int j = 0; j < np; j += U) {
+                float g[U][NACC];
+#pragma unroll
+                for (int t = 0; t < U; ++t) {
+                    const int row = rec[j + t].x;
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k)
+                        g[t][k] = (row >= 0 && lane + 32 * k < C) ? __ldg(a.G + (int64_t)row * C + lane + 32 * k) : 0.f;
+                }
+#pragma unroll
+                for (int t = 0; t < U; ++t) {
+                    if (j + t < np) {                    // warp-uniform
+                        const int2 r = rec[j + t];
+                        const float d = __int_as_float(r.y);
+#pragma unroll
+                        for (int k = 0; k < NACC; ++k) {
+                            if (lane + 32 * k < C) sts_f32(rows_s + 4u * ((j + t) * S + lane + 32 * k), g[t][k]);
+                            if (r.x >= 0) fg[k] = fmaf(g[t][k], d, fg[k]);
+                        }
+                    }
                 }
             }
             __syncwarp();
             // depth grad: one thread, one sequential chain over all C channels
-            if (lane < np && my_p >= 0) {
-                const float4 *g4 = reinterpret_cast<const float4 *>(rows + lane * S);
-                const float4 *f4 = reinterpret_cast<const float4 *>(fs);
+            if (lane < np && cur_p >= 0) {
+                const unsigned ra = rows_s + 4u * (lane * S);
                 float sum = 0.f;
                 for (int i = 0; i < c4; ++i) {
-                    const float4 g = g4[i], f = f4[i];
+                    const float4 g = lds_f4(ra + 16u * i), f = lds_f4(fs_s + 16u * i);
                     sum = fmaf(g.x, f.x, sum);
                     sum = fmaf(g.y, f.y, sum);
                     sum = fmaf(g.z, f.z, sum);
                     sum = fmaf(g.w, f.w, sum);
                 }
-                a.depth_grad[my_p] = sum;
-            }
-            // feat grad: lane per channel, sequential over the points of this pass
-#pragma unroll
-            for (int r = 0; r < NACC; ++r) {
-                const int c = lane + 32 * r;
-                if (c < C) {
-                    float acc = fg[r];
-                    for (int j = 0; j < np; ++j) acc = fmaf(rows[j * S + c], ds[j], acc);
-                    fg[r] = acc;
-                }
+                a.depth_grad[cur_p] = sum;
             }
         }
 #pragma unroll
-        for (int r = 0; r < NACC; ++r) {
-            const int c = lane + 32 * r;
-            if (c < C) a.feat_grad[(int64_t)q * C + c] = fg[r];
+        for (int k = 0; k < NACC; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) a.feat_grad[(int64_t)q * C + c] = fg[k];
         }
     }
 }
@@ -277,7 +319,7 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
     const int64_t pixels = pa.n_bwd;
     if (pixels <= 0) return FO_OK;
     const int C = pa.C;
-    const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C + kPixChunk) * sizeof(float);
+    const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C) * sizeof(float);
     const int nacc = (C + 31) / 32;
     if (vec && nacc <= 4 && smem <= 200 * 1024) {
         const int blocks = grid_for(pixels, kPixWarps, 8);
@@ -347,7 +389,9 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
         ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
         if (smem > 48 * 1024)
             FO_CUDA(cudaFuncSetAttribute(bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bwd_gather_kernel<<<(int)((n_subs + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, smem, stream>>>(ga);
+        const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (n_ctas > 65535 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "grid too large for the gather kernel");
+        bwd_gather_kernel<<<dim3(B, n_ctas), kThreads, smem, stream>>>(ga);
         FO_LAUNCH_CHECK("bwd_gather_kernel");
         pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals;
     } else {
