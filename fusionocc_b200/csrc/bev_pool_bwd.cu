@@ -48,10 +48,11 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 // is read with 128-bit loads, four full 128-byte lines per instruction, a 16-byte chunk being fetched
 // only if one of its four voxels is occupied; it is staged in the swizzled channel-major layout and one
 // compact channels-last row G[k, 0..C) is emitted per interval.
+template <int NACC, bool EXACT>
 __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = a.C;
+    const int C = EXACT ? 32 * NACC : a.C;
     const int sps = a.hdr->subs_per_sample;
     const int b = blockIdx.x;
     const int su = blockIdx.y * kWarpsPerCta + warp;
@@ -77,10 +78,18 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
         if (((occ >> (4 * chunk)) & 0xFu) != 0u) {
             const float *src = plane0 + (int64_t)riq * a.V + 4 * chunk;
             const int64_t step = 4 * a.V;
-            // smem position of logical chunk `chunk` in row r is (chunk ^ r) & 7: two alternating values
-            const unsigned s0 = sbase + ((unsigned)riq << 7) + ((unsigned)((chunk ^ riq) & 7) << 4);
-            const unsigned s1 = sbase + ((unsigned)(riq + 4) << 7) + ((unsigned)((chunk ^ riq ^ 4) & 7) << 4);
+            // smem position of logical chunk `chunk` in row r is (chunk + r) & 7: two alternating values
+            const unsigned s0 = sbase + ((unsigned)riq << 7) + ((unsigned)((chunk + riq) & 7) << 4);
+            const unsigned s1 = sbase + ((unsigned)(riq + 4) << 7) + ((unsigned)((chunk + riq + 4) & 7) << 4);
             int r = riq;
+            for (; r + 28 < C; r += 32, src += 8 * step) {       // eight 128-bit loads in flight per lane
+                float4 x[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) x[t] = __ldcs(reinterpret_cast<const float4 *>(src + t * step));
+                const unsigned o = (unsigned)(r - riq) << 7;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) sts_f4(((t & 1) ? s1 : s0) + o + 1024u * (t >> 1), x[t]);
+            }
             for (; r + 12 < C; r += 16, src += 4 * step) {
                 const float4 x0 = __ldcs(reinterpret_cast<const float4 *>(src));
                 const float4 x1 = __ldcs(reinterpret_cast<const float4 *>(src + step));
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
             }
             for (; r < C; r += 4, src += step) {
                 const float4 x = __ldcs(reinterpret_cast<const float4 *>(src));
-                sts_f4(sbase + ((unsigned)r << 7) + ((unsigned)((chunk ^ r) & 7) << 4), x);
+                sts_f4(sbase + ((unsigned)r << 7) + ((unsigned)((chunk + r) & 7) << 4), x);
             }
         }
     } else {
@@ -100,12 +109,17 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
                 sts_f32(sbase + 4u * stage_index(c, lane), __ldcs(plane0 + (int64_t)c * a.V + lane));
     }
     __syncwarp();
+    // one compact row per interval: lane = channel, conflict-light swizzled read, 128-byte coalesced store
     float *dst = a.G + (int64_t)ia * C + lane;
+    const unsigned lane_row = sbase + ((unsigned)lane << 7);
+    const unsigned lane_rot = ((unsigned)lane & 7u) << 4;
     for (int l = 0; l < ni; ++l, dst += C) {
-        const int v = __shfl_sync(0xffffffffu, my_v, l);
-        if (v < 0) continue;
-        const unsigned off = ((unsigned)lane << 7) + ((((unsigned)(v >> 2) ^ (unsigned)lane) & 7u) << 4) + (((unsigned)v & 3u) << 2);
-        for (int c = lane, k = 0; c < C; c += 32, ++k) dst[32 * k] = lds_f32(sbase + off + 4096u * k);
+        const unsigned v = (unsigned)__shfl_sync(0xffffffffu, my_v, l) & 31u;   // invalid voxels were masked to -1:
+        const bool ok = ((occ >> v) & 1u) != 0u;                                 // they read an unoccupied column
+        const unsigned addr = lane_row + (((v << 2) + lane_rot) & 127u);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+            if (ok && (EXACT || lane + 32 * k < C)) dst[32 * k] = lds_f32(addr + 4096u * k);
     }
 }
 
@@ -124,7 +138,7 @@ struct PixelArgs {
     float *depth_grad, *feat_grad;
 };
 
-constexpr int kPixThreads = 256;
+constexpr int kPixThreads = 128;
 constexpr int kPixWarps   = kPixThreads / 32;
 constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 
@@ -138,35 +152,40 @@ constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 //   depth   lane j owns point j: depth_grad[p_j] = sum_c rows[j][c] * feat[q][c] as ONE sequential FMA
 //           chain over c = 0..C-1 in one thread (bev_pool_cuda.cu:96-101): 2 LDS.128 + 4 FFMA per four
 //           channels for 32 points at once (row stride C+4 keeps the LDS.128 conflict-free).
-// NACC = ceil(C / 32) feat accumulators per lane.  Vector path: C % 4 == 0.
-template <int NACC>
+// NACC = ceil(C / 32) feat accumulators per lane; EXACT: C == 32 * NACC.  Vector path: C % 4 == 0.
+// All indices are 32-bit (the host checks rows * C < 2^31).
+template <int NACC, bool EXACT>
 __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
-    constexpr int U = NACC <= 2 ? 8 : 4;
+    constexpr int U = NACC == 1 ? 16 : (NACC == 2 ? 8 : 4);   // gathered rows in flight per lane
     extern __shared__ __align__(16) float psm[];
-    __shared__ __align__(16) int2 s_rec[kPixWarps][kPixChunk + 8];
+    __shared__ __align__(16) int2 s_rec[kPixWarps][kPixChunk + 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = a.C, c4 = C >> 2, S = C + 4;
-    float *rows = psm + (size_t)warp * (kPixChunk * S + C);                 // [32][S]
+    const int C = EXACT ? 32 * NACC : a.C;
+    const int c4 = C >> 2, S = C + 4;
+    float *rows = psm + warp * (kPixChunk * S + C);                          // [32][S]
     float *fs = rows + kPixChunk * S;                                        // feat row of the pixel [C]
     const unsigned rows_s = (unsigned)__cvta_generic_to_shared(rows);
     const unsigned fs_s = (unsigned)__cvta_generic_to_shared(fs);
+    const unsigned my_col = rows_s + 4u * lane;                              // column `lane` of row 0
     int2 *rec = s_rec[warp];
-    const int64_t n = a.n_bwd_dev ? min((int64_t)max(*a.n_bwd_dev, 0), a.n_bwd) : a.n_bwd;
-    const int64_t warp0 = (int64_t)blockIdx.x * kPixWarps + warp;
-    const int64_t nwarps = (int64_t)gridDim.x * kPixWarps;
+    const int n = a.n_bwd_dev ? min(max(*a.n_bwd_dev, 0), (int)a.n_bwd) : (int)a.n_bwd;
+    const int warp0 = blockIdx.x * kPixWarps + warp;
+    const int nwarps = gridDim.x * kPixWarps;
+    const int n_depth = (int)a.n_depth, n_rows_G = (int)a.n_rows_G, n_iv = (int)a.n_iv;
 
-    for (int64_t m = warp0; m < n; m += nwarps) {
+    for (int m = warp0; m < n; m += nwarps) {
         const int s = __ldg(a.bwd_starts + m), len = __ldg(a.bwd_lengths + m);
         const int q = __ldg(a.bwd_ids + m);
         if (len <= 0 || s < 0 || (int64_t)s + len > a.n_entries || q < 0 || q >= a.n_feat_rows) continue;
+        const int32_t *ep = a.ent_p + s, *ei = a.ent_iv + s;
         auto load_rec = [&](int j0, int &p_out) -> int2 {
             int2 r = make_int2(-1, 0);                    // (G row or -1, depth bits)
             p_out = -1;
             if (j0 + lane < len) {
-                int p = __ldg(a.ent_p + s + j0 + lane);
-                int row = __ldg(a.ent_iv + s + j0 + lane);
-                if (a.row_map) row = (row >= 0 && row < a.n_iv) ? __ldg(a.row_map + row) : -1;
-                if (p >= 0 && p < a.n_depth && row >= 0 && row < a.n_rows_G) {
+                const int p = __ldg(ep + j0 + lane);
+                int row = __ldg(ei + j0 + lane);
+                if (a.row_map) row = ((unsigned)row < (unsigned)n_iv) ? __ldg(a.row_map + row) : -1;
+                if ((unsigned)p < (unsigned)n_depth && (unsigned)row < (unsigned)n_rows_G) {
                     r.x = row;
                     r.y = __float_as_int(__ldg(a.depth + p));
                     p_out = p;
@@ -177,8 +196,7 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
         int my_p;
         int2 mine = load_rec(0, my_p);
         __syncwarp();
-        for (int i = lane; i < c4; i += 32)
-            reinterpret_cast<float4 *>(fs)[i] = ldg4(a.feat + ((int64_t)q * c4 + i) * 4);
+        for (int i = lane; i < c4; i += 32) reinterpret_cast<float4 *>(fs)[i] = ldg4(a.feat + (q * c4 + i) * 4);
         float fg[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) fg[k] = 0.f;
@@ -188,28 +206,30 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
             const int cur_p = my_p;
             __syncwarp();                               // previous pass finished reading rows / rec
             rec[lane] = mine;
-            if (lane < 8) rec[kPixChunk + lane] = make_int2(-1, 0);
+            if (lane < 16) rec[kPixChunk + lane] = make_int2(-1, 0);
             __syncwarp();
             if (j0 + kPixChunk < len) mine = load_rec(j0 + kPixChunk, my_p);
             for (int j = 0; j < np; j += U) {
                 float g[U][NACC];
+                int2 r[U];
+#pragma unroll
+                for (int t = 0; t < U; ++t) r[t] = rec[j + t];
 #pragma unroll
                 for (int t = 0; t < U; ++t) {
-                    const int row = rec[j + t].x;
+                    const int base = max(r[t].x, 0) * C + lane;      // invalid rows read row 0 and are discarded
 #pragma unroll
-                    for (int k = 0; k < NACC; ++k)
-                        g[t][k] = (row >= 0 && lane + 32 * k < C) ? __ldg(a.G + (int64_t)row * C + lane + 32 * k) : 0.f;
+                    for (int k = 0; k < NACC; ++k) g[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.G + base + 32 * k) : 0.f;
                 }
+                const unsigned dst = my_col + 4u * (j * S);
 #pragma unroll
                 for (int t = 0; t < U; ++t) {
-                    if (j + t < np) {                    // warp-uniform
-                        const int2 r = rec[j + t];
-                        const float d = __int_as_float(r.y);
+                    const bool ok = r[t].x >= 0;          // warp-uniform; padding records are invalid
+                    const float d = __int_as_float(r[t].y);
 #pragma unroll
-                        for (int k = 0; k < NACC; ++k) {
-                            if (lane + 32 * k < C) sts_f32(rows_s + 4u * ((j + t) * S + lane + 32 * k), g[t][k]);
-                            if (r.x >= 0) fg[k] = fmaf(g[t][k], d, fg[k]);
-                        }
+                    for (int k = 0; k < NACC; ++k) {
+                        if (EXACT || lane + 32 * k < C) sts_f32(dst + 4u * (t * S + 32 * k), g[t][k]);
+                        const float x = fmaf(g[t][k], d, fg[k]);
+                        fg[k] = ok ? x : fg[k];
                     }
                 }
             }
@@ -218,6 +238,7 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
             if (lane < np && cur_p >= 0) {
                 const unsigned ra = rows_s + 4u * (lane * S);
                 float sum = 0.f;
+#pragma unroll 2
                 for (int i = 0; i < c4; ++i) {
                     const float4 g = lds_f4(ra + 16u * i), f = lds_f4(fs_s + 16u * i);
                     sum = fmaf(g.x, f.x, sum);
@@ -228,11 +249,10 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
                 a.depth_grad[cur_p] = sum;
             }
         }
+        float *fgp = a.feat_grad + q * C + lane;
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            const int c = lane + 32 * k;
-            if (c < C) a.feat_grad[(int64_t)q * C + c] = fg[k];
-        }
+        for (int k = 0; k < NACC; ++k)
+            if (EXACT || lane + 32 * k < C) fgp[32 * k] = fg[k];
     }
 }
 
@@ -321,20 +341,30 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
     const int C = pa.C;
     const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C) * sizeof(float);
     const int nacc = (C + 31) / 32;
-    if (vec && nacc <= 4 && smem <= 200 * 1024) {
+    const bool idx32 = pa.n_rows_G * C < INT_MAX && pa.n_feat_rows * C < INT_MAX && pixels < INT_MAX;
+    if (vec && idx32 && nacc <= 4 && smem <= 200 * 1024) {
         const int blocks = grid_for(pixels, kPixWarps, 8);
-#define FO_PIX(NA)                                                                                           \
-    do {                                                                                                     \
-        if (smem > 48 * 1024)                                                                                \
-            FO_CUDA(cudaFuncSetAttribute(bwd_pixel_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         (int)smem));                                                        \
-        bwd_pixel_kernel<NA><<<blocks, kPixThreads, smem, stream>>>(pa);                                     \
+#define FO_PIX(NA, EX)                                                                                          \
+    do {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                   \
+            FO_CUDA(cudaFuncSetAttribute(bwd_pixel_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                           \
+        bwd_pixel_kernel<NA, EX><<<blocks, kPixThreads, smem, stream>>>(pa);                                    \
     } while (0)
-        switch (nacc) {
-            case 1: FO_PIX(1); break;
-            case 2: FO_PIX(2); break;
-            case 3: FO_PIX(3); break;
-            default: FO_PIX(4); break;
+        if (C % 32 == 0) {
+            switch (nacc) {
+                case 1: FO_PIX(1, true); break;
+                case 2: FO_PIX(2, true); break;
+                case 3: FO_PIX(3, true); break;
+                default: FO_PIX(4, true); break;
+            }
+        } else {
+            switch (nacc) {
+                case 1: FO_PIX(1, false); break;
+                case 2: FO_PIX(2, false); break;
+                case 3: FO_PIX(3, false); break;
+                default: FO_PIX(4, false); break;
+            }
         }
 #undef FO_PIX
     } else {
@@ -387,11 +417,37 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
         GatherArgs ga;
         ga.og = out_grad; ga.C = c; ga.V = n_vox;
         ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
-        if (smem > 48 * 1024)
-            FO_CUDA(cudaFuncSetAttribute(bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
-        if (n_ctas > 65535 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "grid too large for the gather kernel");
-        bwd_gather_kernel<<<dim3(B, n_ctas), kThreads, smem, stream>>>(ga);
+        if (n_ctas > 65535 || B > 65535 || c > 256)
+            return set_error(FO_ERR_UNSUPPORTED, "grid or channel count too large for the gather kernel");
+#define FO_GATHER(NA, EX)                                                                                     \
+    do {                                                                                                      \
+        if (smem > 48 * 1024)                                                                                 \
+            FO_CUDA(cudaFuncSetAttribute(bwd_gather_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                         \
+        bwd_gather_kernel<NA, EX><<<dim3(B, n_ctas), kThreads, smem, stream>>>(ga);                           \
+    } while (0)
+        const int nacc = (c + 31) / 32;
+        if (c % 32 == 0 && nacc <= 4) {
+            switch (nacc) {
+                case 1: FO_GATHER(1, true); break;
+                case 2: FO_GATHER(2, true); break;
+                case 3: FO_GATHER(3, true); break;
+                default: FO_GATHER(4, true); break;
+            }
+        } else {
+            switch (nacc) {
+                case 1: FO_GATHER(1, false); break;
+                case 2: FO_GATHER(2, false); break;
+                case 3: FO_GATHER(3, false); break;
+                case 4: FO_GATHER(4, false); break;
+                case 5: FO_GATHER(5, false); break;
+                case 6: FO_GATHER(6, false); break;
+                case 7: FO_GATHER(7, false); break;
+                default: FO_GATHER(8, false); break;
+            }
+        }
+#undef FO_GATHER
         FO_LAUNCH_CHECK("bwd_gather_kernel");
         pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals;
     } else {

@@ -64,35 +64,46 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = EXACT ? 32 * NACC : a.C;
-    // grid = (B, ceil(subs_per_sample / 4)): x-fastest block order interleaves the samples, so the dense
-    // near-ego regions of all samples are reached at the same relative time
+    // grid = (B, ceil(subs_per_sample / warps)): x-fastest block order interleaves the samples, so the
+    // dense near-ego regions of all samples are reached at the same relative time
     const int sps = a.hdr->subs_per_sample;
     const int b = blockIdx.x;
     const int su = blockIdx.y * kWarpsPerCta + warp;
     if (su >= sps) return;
     const int u = b * sps + su;
-    const int v0 = su << kSubShift;
-    const int nv = (int)min((int64_t)kSub, a.V - v0);
     const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
-    const int vbase = (int)((int64_t)b * a.V) + v0;      // global voxel id of the sub-tile's first voxel (< 2^31)
+    const int v0 = su << kSubShift;
+    const int nv = min(kSub, (int)a.V - v0);
+    const int vbase = b * (int)a.V + v0;                 // global voxel id of the sub-tile's first voxel (< 2^31)
     const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((a.V & 3) == 0);
-    float *plane0 = a.out + ((int64_t)b * C) * a.V + v0;
     const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
+    const int64_t V = a.V;
+    float *pl = a.out + ((int64_t)b * C + riq) * V + v0; // row riq of this sub-tile's block
 
     if (pa >= pb && vec_out) {                            // empty sub-tile: stream zeros, no staging
         if (4 * chunk < nv) {
-            float *dst = plane0 + (int64_t)riq * a.V + 4 * chunk;
-            const int64_t step = 4 * a.V;
+            float *dst = pl + 4 * chunk;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = riq; r < C; r += 4, dst += step) __stcs(reinterpret_cast<float4 *>(dst), zero4);
+            if (EXACT) {
+#pragma unroll
+                for (int i = 0; i < 8 * NACC; ++i) __stcs(reinterpret_cast<float4 *>(dst + (4 * i) * V), zero4);
+            } else {
+                for (int r = riq; r < C; r += 4, dst += 4 * V) __stcs(reinterpret_cast<float4 *>(dst), zero4);
+            }
         }
         return;
     }
     float *stage = smem + warp * C * kSub;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
-    for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
+    } else {
+        for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
+    }
     int2 *rec = s_rec[warp];
     const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
+    const unsigned lane_rot = ((unsigned)lane & 7u) << 4;             // its rotation, in bytes
 
     auto load_rec = [&](int i0) -> int2 {
         int2 m = make_int2(0, 0);                         // (feature row << 5 | voxel in sub-tile, depth bits)
@@ -109,32 +120,33 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
     int cur_v = -1;
     auto flush = [&]() {
-        const unsigned off = ((((unsigned)(cur_v >> 2) ^ (unsigned)lane) & 7u) << 4) + (((unsigned)cur_v & 3u) << 2);
+        const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
 #pragma unroll
         for (int k = 0; k < NACC; ++k)
             if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
     };
-    auto load_group = [&](float (&f)[U][NACC], int j) {
+    auto load_group = [&](float (&f)[U][NACC], int2 (&r)[U], int j) {
+#pragma unroll
+        for (int t = 0; t < U; ++t) r[t] = rec[j + t];
 #pragma unroll
         for (int t = 0; t < U; ++t) {
-            const int row = (rec[j + t].x >> kSubShift) * C + lane;
+            const int row = (r[t].x >> kSubShift) * C + lane;
 #pragma unroll
             for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
         }
     };
-    auto consume = [&](const float (&f)[U][NACC], int j, int count) {
+    auto consume = [&](const float (&f)[U][NACC], const int2 (&r)[U], int count) {
 #pragma unroll
         for (int t = 0; t < U; ++t) {
-            if (t < count) {                              // warp-uniform
-                const int2 r = rec[j + t];
-                const int v = r.x & (kSub - 1);
+            if (t < count) {                              // warp-uniform (compile-time true for full groups)
+                const int v = r[t].x & (kSub - 1);
                 if (v != cur_v) {                         // warp-uniform: a new interval starts
                     if (cur_v >= 0) flush();
 #pragma unroll
                     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
                     cur_v = v;
                 }
-                const float d = __int_as_float(r.y);
+                const float d = __int_as_float(r[t].y);
 #pragma unroll
                 for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d, acc[k]);
             }
@@ -151,21 +163,22 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
         if (i0 + 32 < pb) mine = load_rec(i0 + 32);       // next batch's records fly during this batch
         const int nfull = n & ~(U - 1);
         float fa[U][NACC], fb[U][NACC];
+        int2 ra[U], rb2[U];
         if (nfull) {
-            load_group(fa, 0);
+            load_group(fa, ra, 0);
             for (int j = 0; j < nfull; j += 2 * U) {
                 const bool has_b = j + U < nfull;
-                if (has_b) load_group(fb, j + U);
-                consume(fa, j, U);
+                if (has_b) load_group(fb, rb2, j + U);
+                consume(fa, ra, U);
                 if (has_b) {
-                    if (j + 2 * U < nfull) load_group(fa, j + 2 * U);
-                    consume(fb, j + U, U);
+                    if (j + 2 * U < nfull) load_group(fa, ra, j + 2 * U);
+                    consume(fb, rb2, U);
                 }
             }
         }
         if (nfull < n) {                                  // remainder group: rows of padding records are row 0
-            load_group(fa, nfull);
-            consume(fa, nfull, n - nfull);
+            load_group(fa, ra, nfull);
+            consume(fa, ra, n - nfull);
         }
     }
     if (cur_v >= 0) flush();
@@ -174,26 +187,36 @@ __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
     if (LAYOUT == FO_LAYOUT_BCZYX) {
         if (vec_out) {
             // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
-            // logical chunk stored at smem position `chunk` of row r is (chunk ^ r) & 7: it alternates
+            // logical chunk stored at smem position `chunk` of row r is (chunk - r) & 7: it alternates
             // between two values as r advances by 4.
-            const int ck0 = (chunk ^ riq) & 7, ck1 = ck0 ^ 4;
-            float *d0 = plane0 + (int64_t)riq * a.V + 4 * ck0;
-            float *d1 = plane0 + (int64_t)(riq + 4) * a.V + 4 * ck1;
-            const int64_t step = 8 * a.V;
-            unsigned sa = sbase + ((unsigned)riq << 7) + ((unsigned)chunk << 4);
+            const int ck0 = (chunk - riq) & 7, ck1 = ck0 ^ 4;
+            float *d0 = pl + 4 * ck0;
+            float *d1 = pl + 4 * V + 4 * ck1;
+            const unsigned sa = sbase + 16u * lane;       // row riq, position chunk
             const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
-            for (int r = riq; r < C; r += 8, d0 += step, d1 += step, sa += 1024u) {
-                const float4 x0 = lds_f4(sa);
-                if (w0) __stcs(reinterpret_cast<float4 *>(d0), x0);
-                if (r + 4 < C) {
-                    const float4 x1 = lds_f4(sa + 512u);
-                    if (w1) __stcs(reinterpret_cast<float4 *>(d1), x1);
+            if (EXACT) {
+#pragma unroll
+                for (int i = 0; i < 4 * NACC; ++i) {
+                    const float4 x0 = lds_f4(sa + 1024u * i);
+                    const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
+                    if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
+                }
+            } else {
+                for (int r = riq, i = 0; r < C; r += 8, ++i) {
+                    const float4 x0 = lds_f4(sa + 1024u * i);
+                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
+                    if (r + 4 < C) {
+                        const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                        if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
+                    }
                 }
             }
         } else {
+            float *plane0 = a.out + ((int64_t)b * C) * V + v0;
             for (int e = lane; e < C * kSub; e += 32) {
                 const int c = e >> kSubShift, v = e & (kSub - 1);
-                if (v < nv) __stcs(plane0 + (int64_t)c * a.V + v, stage[stage_index(c, v)]);
+                if (v < nv) __stcs(plane0 + (int64_t)c * V + v, stage[stage_index(c, v)]);
             }
         }
     } else {

@@ -18,8 +18,10 @@ namespace fo {
 // Tiling constants shared by the forward plan, the forward kernel and the backward gather.
 // The unit of work is a SUB-TILE: kSub = 32 consecutive voxels of ONE sample in flattened (z,y,x)
 // order, owned by one warp; in the (B,C,Z,Y,X) tensor that is C runs of 128 contiguous bytes (one full
-// cache line each).  A CTA is four warps = four consecutive sub-tiles (512 contiguous bytes per channel
-// plane), with no block-level synchronisation at all.
+// cache line each).  A CTA is two warps = two consecutive sub-tiles, with no block-level
+// synchronisation at all.  Small CTAs on purpose: sub-tile costs are very uneven (0 .. 844 points), and a
+// CTA keeps its shared memory and registers until its slowest warp is done; with four warps per CTA a
+// third of the resident warps were such "zombies" (achieved occupancy 40 % of 62 % theoretical).
 //
 // Why (measured, profiles/r01): the first tile-per-CTA designs were issue-bound, ~2750 warp
 // instructions per 128 voxels, because 8-lane groups each re-derived indices for one interval.  Points
@@ -29,7 +31,7 @@ namespace fo {
 // ----------------------------------------------------------------------------------------------
 constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
 constexpr int kSubShift     = 5;
-constexpr int kThreads      = 128;   // threads per CTA of the tile kernels
+constexpr int kThreads      = 64;    // threads per CTA of the tile kernels (see below)
 constexpr int kWarpsPerCta  = kThreads / 32;
 
 // Forward-plan flags (device side, FwdPlanHeader::flags)
@@ -196,14 +198,12 @@ __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpre
 
 // Per-warp shared-memory stage of one sub-tile: channel-major [C][kSub] floats = the layout of the
 // (B,C,Z,Y,X) block itself, so it is drained / filled with LDS.128/STS.128 <-> 128-bit global
-// accesses.  The 16-byte chunk index inside a row is XOR-ed with (c & 7): a flush of one voxel's 32
-// channels (lane = channel) then spreads over 8 bank groups instead of hammering one bank.
+// accesses.  Row c is ROTATED by (c & 7) 16-byte chunks: a flush of one voxel's channels (lane =
+// channel) then spreads over 8 bank groups instead of hammering one bank, the rotation costs three
+// integer instructions, and 4-voxel chunks stay intact for the 128-bit accesses.
 __device__ __forceinline__ int stage_index(int c, int v) {
-    return (c << kSubShift) + ((((v >> 2) ^ c) & 7) << 2) + (v & 3);
+    return (c << kSubShift) + ((v + ((c & 7) << 2)) & (kSub - 1));
 }
-
-// streaming (evict-first) store: the dense voxel tensor is written once and not re-read here
-__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
 #endif
 
 }  // namespace fo
