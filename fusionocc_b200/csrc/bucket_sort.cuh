@@ -22,11 +22,9 @@
 
 namespace fo {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 128;
 constexpr int kScanItems   = 16;                          // buckets per thread (4 x int4)
-constexpr int kScanTile    = kScanThreads * kScanItems;   // 4096 buckets per CTA
-constexpr int kScanShift   = 12;
-static_assert((1 << kScanShift) == kScanTile, "scan tile shift");
+constexpr int kScanTile    = kScanThreads * kScanItems;   // 2048 buckets per CTA
 
 // Per-scan-tile aggregates (points << 32 | non-empty buckets) come from a separate reduce pass over the
 // counter array (coalesced int4 reads, the array is L2-resident right after the count pass), so the scan
@@ -214,14 +212,26 @@ __device__ inline void warp_sort_segment(int32_t *seg, int len, int *smem /* kSo
         int v[4], rank[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) { v[r] = (lane + 32 * r < len) ? seg[lane + 32 * r] : INT_MAX; rank[r] = 0; }
+        if (len <= 64) {
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            if (32 * rr < len) {
+            for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll 8
                 for (int l = 0; l < 32; ++l) {
                     const int other = __shfl_sync(0xffffffffu, v[rr], l);
+                    rank[0] += (other < v[0]) ? 1 : 0;
+                    rank[1] += (other < v[1]) ? 1 : 0;
+                }
+            }
+        } else {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) rank[r] += (other < v[r]) ? 1 : 0;
+            for (int rr = 0; rr < 4; ++rr) {
+                if (32 * rr < len) {
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) {
+                        const int other = __shfl_sync(0xffffffffu, v[rr], l);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) rank[r] += (other < v[r]) ? 1 : 0;
+                    }
                 }
             }
         }

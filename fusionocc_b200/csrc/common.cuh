@@ -126,7 +126,7 @@ struct BwdPlanView {
     int64_t cap;
 };
 __host__ inline size_t bucket_zero_bytes(int64_t n_buckets) {
-    const int64_t n_scan_tiles = (n_buckets + 4095) / 4096;
+    const int64_t n_scan_tiles = (n_buckets + 2047) / 2048;
     return (size_t)(align_up(n_buckets * 4, 256) + align_up(n_scan_tiles * 8, 256) + 256);
 }
 __host__ inline size_t bwd_plan_fixed_bytes(int64_t rows) {

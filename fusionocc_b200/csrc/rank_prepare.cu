@@ -218,6 +218,76 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     }
 }
 
+// Same job with a bitonic network over packed keys (position << 7 | depth slot): 25 shuffle stages x R
+// registers instead of 32 x R broadcasts x R compares.  Needs positions < 2^24 (n_depth < 2^24) and D <= 128.
+template <int R>   // R in {1, 2, 4}: 32 * R >= D
+__global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
+    const int32_t *__restrict__ pt2pos, const int32_t *__restrict__ pos2iv, int D, int HW, int n_rows,
+    BwdPlanHeader *hdr, int32_t *ent_p, int32_t *ent_iv, int32_t *starts, int32_t *lengths, int32_t *ids,
+    const int32_t *n_points_dev) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->n_bwd_intervals = n_rows;
+        hdr->n_points = n_points_dev ? *n_points_dev : 0;
+    }
+    for (int q = warp0; q < n_rows; q += nwarps) {
+        const int bn = q / HW, hw = q - bn * HW;
+        const int pbase = bn * D * HW + hw;
+        int key[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int d = lane + 32 * r;                 // element index e = 32 r + lane holds depth slot d = e
+            key[r] = INT_MAX;
+            if (d < D) {
+                const int v = __ldg(pt2pos + pbase + d * HW);
+                if (v >= 0) key[r] = (v << 7) | d;
+            }
+        }
+        // bitonic sort, ascending, over n = 32 R elements; element e = 32 r + lane
+#pragma unroll
+        for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {                           // partner in another register of the same lane
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int pr = r ^ (j >> 5);
+                        if (pr > r) {
+                            const bool up = (((32 * r) & k) == 0);
+                            const int lo = min(key[r], key[pr]), hi = max(key[r], key[pr]);
+                            key[r] = up ? lo : hi;
+                            key[pr] = up ? hi : lo;
+                        }
+                    }
+                } else {                                 // partner in lane ^ j, same register
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                        const bool up = ((((32 * r) | lane) & k) == 0);
+                        const bool lower = (lane & j) == 0;
+                        key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                    }
+                }
+            }
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (key[r] != INT_MAX) {
+                const int e = 32 * r + lane;
+                ent_p[q * D + e] = pbase + (key[r] & 127) * HW;
+                ent_iv[q * D + e] = __ldg(pos2iv + (key[r] >> 7));
+                ++cnt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) { starts[q] = q * D; lengths[q] = cnt; ids[q] = q; }
+    }
+}
+
 // Generic build, last step: sorted forward positions -> (depth index, forward interval) entries.
 __global__ void __launch_bounds__(256) bwd_plan_fill_entries_kernel(const int32_t *__restrict__ pos,
                                                                     const int32_t *__restrict__ rd,
@@ -278,7 +348,7 @@ SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     s.zero_bytes = (size_t)(p - (char *)base);
     return s;
 }
-static_assert(kScanTile == 4096, "bucket_zero_bytes() in common.cuh assumes 4096-bucket scan tiles");
+static_assert(kScanTile == 2048, "bucket_zero_bytes() in common.cuh assumes 2048-bucket scan tiles");
 }  // namespace
 
 // exported for the other translation units
@@ -383,7 +453,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     const int64_t cap_iv = P < NV ? P : NV;
     order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<fwd>");
-    order_long_kernel<true><<<148 * 4, kSortThreads, 0, stream>>>(oa);
+    order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<fwd>");
     return FO_OK;
 }
@@ -418,6 +488,19 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
         const int R = (D + 31) / 32;
         if (R > 8) return set_error(FO_ERR_UNSUPPORTED, "structured backward plan supports D <= 256 (got %d)", D);
         const int blocks = grid_for(n_feat_rows * 32, 256, 8);
+        if (D <= 128 && n_depth < (1 << 24)) {          // packed-key bitonic variant
+#define FO_BITONIC(RR)                                                                                          \
+    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2pos, fv.pos2iv, D, hw,             \
+                                                                      (int)n_feat_rows, bv.hdr, bv.ent_p,      \
+                                                                      bv.ent_iv, bv.starts, bv.lengths, bv.ids, \
+                                                                      n_points_dev)
+            if (R == 1) FO_BITONIC(1);
+            else if (R == 2) FO_BITONIC(2);
+            else FO_BITONIC(4);
+#undef FO_BITONIC
+            FO_LAUNCH_CHECK("bwd_plan_structured_bitonic_kernel");
+            return FO_OK;
+        }
 #define FO_STRUCT(RR)                                                                                         \
     bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2pos, fv.pos2iv, D, hw, (int)n_feat_rows, \
                                                               bv.hdr, bv.ent_p, bv.ent_iv, bv.starts,        \
@@ -467,7 +550,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     oa.long_list = bv.slot; oa.long_count = ss.counter;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<bwd>");
-    order_long_kernel<false><<<148 * 4, kSortThreads, 0, stream>>>(oa);
+    order_long_kernel<false><<<148 * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<bwd>");
     bwd_plan_fill_entries_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(bv.pos, ranks_depth, fv.pos2iv, bv.hdr,
                                                                               bv.cap, bv.ent_p, bv.ent_iv);
