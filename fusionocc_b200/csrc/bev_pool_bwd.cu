@@ -138,7 +138,10 @@ struct PixelArgs {
     float *depth_grad, *feat_grad;
 };
 
-constexpr int kPixThreads = 128;
+#ifndef FO_PIX_THREADS
+#define FO_PIX_THREADS 256
+#endif
+constexpr int kPixThreads = FO_PIX_THREADS;
 constexpr int kPixWarps   = kPixThreads / 32;
 constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 

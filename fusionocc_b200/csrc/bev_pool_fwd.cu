@@ -57,7 +57,10 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 // (2*U rows in flight per lane), and the next 32 records are fetched while a batch is processed.
 template <int NACC, bool EXACT, int LAYOUT>
 __global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
-    constexpr int U = NACC <= 2 ? 8 : 4;                 // feature rows per group
+#ifndef FO_FWD_U
+#define FO_FWD_U 8
+#endif
+    constexpr int U = NACC <= 2 ? FO_FWD_U : 4;          // feature rows per group
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(16) int2 s_rec[kWarpsPerCta][32 + 8];
     if (a.hdr->flags & kFlagUnsorted) return;            // the order-agnostic path runs instead

@@ -18,10 +18,12 @@ namespace fo {
 // Tiling constants shared by the forward plan, the forward kernel and the backward gather.
 // The unit of work is a SUB-TILE: kSub = 32 consecutive voxels of ONE sample in flattened (z,y,x)
 // order, owned by one warp; in the (B,C,Z,Y,X) tensor that is C runs of 128 contiguous bytes (one full
-// cache line each).  A CTA is two warps = two consecutive sub-tiles, with no block-level
-// synchronisation at all.  Small CTAs on purpose: sub-tile costs are very uneven (0 .. 844 points), and a
-// CTA keeps its shared memory and registers until its slowest warp is done; with four warps per CTA a
-// third of the resident warps were such "zombies" (achieved occupancy 40 % of 62 % theoretical).
+// cache line each).  A CTA is ONE warp, with no block-level synchronisation at all.  Single-warp CTAs on
+// purpose: sub-tile costs are very uneven (0 .. 844 points), and a CTA keeps its shared memory and
+// registers until its slowest warp is done; with four warps per CTA a third of the resident warps were
+// such "zombies" (achieved occupancy 40 % of 62 % theoretical).  Measured (profiles/r01, forward /
+// backward at the headline shape, batch 8): 128 threads 185 / 245 us, 64 threads 173 / 243 us,
+// 32 threads 152 / 208 us.
 //
 // Why (measured, profiles/r01): the first tile-per-CTA designs were issue-bound, ~2750 warp
 // instructions per 128 voxels, because 8-lane groups each re-derived indices for one interval.  Points
@@ -31,7 +33,10 @@ namespace fo {
 // ----------------------------------------------------------------------------------------------
 constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
 constexpr int kSubShift     = 5;
-constexpr int kThreads      = 64;    // threads per CTA of the tile kernels (see below)
+#ifndef FO_TILE_THREADS
+#define FO_TILE_THREADS 32
+#endif
+constexpr int kThreads      = FO_TILE_THREADS;    // threads per CTA of the tile kernels (see below)
 constexpr int kWarpsPerCta  = kThreads / 32;
 
 // Forward-plan flags (device side, FwdPlanHeader::flags)
