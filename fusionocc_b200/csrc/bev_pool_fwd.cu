@@ -55,8 +55,11 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 // records, no shuffles), shared-memory addresses are precomputed 32-bit values, feature rows are
 // fetched in groups of U with the NEXT group already in flight while the current one is consumed
 // (2*U rows in flight per lane), and the next 32 records are fetched while a batch is processed.
+#ifndef FO_FWD_MIN_CTAS
+#define FO_FWD_MIN_CTAS 1
+#endif
 template <int NACC, bool EXACT, int LAYOUT>
-__global__ void __launch_bounds__(kThreads) fwd_dense_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
 #ifndef FO_FWD_U
 #define FO_FWD_U 8
 #endif

@@ -27,7 +27,7 @@ using namespace fo;
 extern "C" int fo_abi_version(void) { return FO_ABI_VERSION; }
 extern "C" const char *fo_last_error(void) { return g_err; }
 extern "C" const char *fo_build_info(void) {
-    return "fusionocc_b200 abi=1 arch=sm_100a tile=128 threads=256 group=8xfloat4 cuda=" FO_STR_CUDA_VERSION;
+    return "fusionocc_b200 abi=1 arch=sm_100a subtile=32vox cta=1warp lanes=channels cuda=" FO_STR_CUDA_VERSION;
 }
 
 // ------------------------------------------------------------------------------------------------
