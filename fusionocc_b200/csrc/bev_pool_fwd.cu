@@ -32,6 +32,8 @@ struct FwdArgs {
     float *out;
     const FwdPlanHeader *hdr;
     const int32_t *sub_pt;
+    int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
+    int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
 };
 
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
@@ -56,182 +58,244 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 // fetched in groups of U with the NEXT group already in flight while the current one is consumed
 // (2*U rows in flight per lane), and the next 32 records are fetched while a batch is processed.
 #ifndef FO_FWD_MIN_CTAS
-#define FO_FWD_MIN_CTAS 1
+#define FO_FWD_MIN_CTAS 32          // <= 64 registers: 32 single-warp CTAs per SM
 #endif
-template <int NACC, bool EXACT, int LAYOUT>
-__global__ void __launch_bounds__(kThreads, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
 #ifndef FO_FWD_U
 #define FO_FWD_U 8
 #endif
+#ifndef FO_FWD_RUN
+#define FO_FWD_RUN 1
+#endif
+constexpr int kRun = FO_FWD_RUN;     // consecutive sub-tiles of one sample per warp (<= 31)
+
+// A warp owns a run of kRun consecutive sub-tiles (kRun = 1 in the shipped build).  The dependent chain
+//     point range -> rank records -> depth -> feature rows
+// is walked with as few round trips as possible: the plan's flag word and the point range are independent
+// loads (sub-tiles per sample is a kernel argument), the three record arrays are fetched together, and for a
+// run the first three links are walked once for all its sub-tiles.
+//
+// Measured on a B200 (headline shape, batch 8, profiles/r01_summary.md "forward experiments"): this kernel
+// wants MANY SHORT-LIVED warps.  kRun = 1 / 2 / 4 / 8: 149 / 154 / 160 / 197 us; a persistent variant with a
+// 4-deep software pipeline across sub-tiles (work tickets): 185 us, 308 us on an all-empty grid; 21 instead
+// of 32 resident CTAs per SM: 159 -> 149 us; streaming (evict-first) stores 149 us vs 169 us for write-back,
+// .cg or .wt stores.  Everything that makes a warp hold its slot longer, or spreads the lines written at
+// one time over a wider address window, loses more DRAM write efficiency than the saved latency gains.
+template <int NACC, bool EXACT, int LAYOUT>
+__global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
     constexpr int U = NACC <= 2 ? FO_FWD_U : 4;          // feature rows per group
-    extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(16) int2 s_rec[kWarpsPerCta][32 + 8];
-    if (a.hdr->flags & kFlagUnsorted) return;            // the order-agnostic path runs instead
+    extern __shared__ __align__(16) float smem[];        // stage [C][32]
+    __shared__ __align__(16) int s_rx[kRun + 1][32 + 8];     // (feature row << 5 | voxel slot) per point
+    __shared__ __align__(16) float s_rd[kRun + 1][32 + 8];   // depth value per point; row kRun: later batches
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
     const int C = EXACT ? 32 * NACC : a.C;
-    // grid = (B, ceil(subs_per_sample / warps)): x-fastest block order interleaves the samples, so the
+    // grid = (B, ceil(subs_per_sample / kRun)): x-fastest block order interleaves the samples, so the
     // dense near-ego regions of all samples are reached at the same relative time
-    const int sps = a.hdr->subs_per_sample;
+    const int sps = a.sps;
     const int b = blockIdx.x;
-    const int su = blockIdx.y * kWarpsPerCta + warp;
-    if (su >= sps) return;
-    const int u = b * sps + su;
-    const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
-    const int v0 = su << kSubShift;
-    const int nv = min(kSub, (int)a.V - v0);
-    const int vbase = b * (int)a.V + v0;                 // global voxel id of the sub-tile's first voxel (< 2^31)
-    const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((a.V & 3) == 0);
-    const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
+    const int su0 = blockIdx.y * kRun;
+    const int nrun = min(kRun, sps - su0);
+    // one round trip: the plan's flag word and the run's point ranges are independent loads
+    const int flags = a.check_flags ? __ldg(&a.hdr->flags) : 0;
+    int my_pt = 0;
+    if (lane <= nrun) my_pt = __ldg(a.sub_pt + b * sps + su0 + lane);
+    if (flags & kFlagUnsorted) return;                   // the order-agnostic path runs instead
     const int64_t V = a.V;
-    float *pl = a.out + ((int64_t)b * C + riq) * V + v0; // row riq of this sub-tile's block
-
-    if (pa >= pb && vec_out) {                            // empty sub-tile: stream zeros, no staging
-        if (4 * chunk < nv) {
-            float *dst = pl + 4 * chunk;
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EXACT) {
-#pragma unroll
-                for (int i = 0; i < 8 * NACC; ++i) __stcs(reinterpret_cast<float4 *>(dst + (4 * i) * V), zero4);
-            } else {
-                for (int r = riq; r < C; r += 4, dst += 4 * V) __stcs(reinterpret_cast<float4 *>(dst), zero4);
-            }
-        }
-        return;
-    }
-    float *stage = smem + warp * C * kSub;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
-    if (EXACT) {
-#pragma unroll
-        for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
-    } else {
-        for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
-    }
-    int2 *rec = s_rec[warp];
+    const int bV = b * (int)V;                           // global voxel id of the sample's first voxel (< 2^31)
+    const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((V & 3) == 0);
+    const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
     const unsigned lane_rot = ((unsigned)lane & 7u) << 4;             // its rotation, in bytes
 
-    auto load_rec = [&](int i0) -> int2 {
-        int2 m = make_int2(0, 0);                         // (feature row << 5 | voxel in sub-tile, depth bits)
-        if (i0 + lane < pb) {
-            const int q = __ldg(a.rf + i0 + lane);
-            const int v = __ldg(a.rb + i0 + lane) - vbase;
-            m.x = (q << kSubShift) | (v & (kSub - 1));
-            m.y = __float_as_int(__ldg(a.depth + __ldg(a.rd + i0 + lane)));
-        }
-        return m;
-    };
-    float acc[NACC];
+    // ---- the run's first-batch records: everything in flight at once ----
+    {
+        int mx[kRun], mr[kRun];
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-    int cur_v = -1;
-    auto flush = [&]() {
-        const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
-#pragma unroll
-        for (int k = 0; k < NACC; ++k)
-            if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
-    };
-    auto load_group = [&](float (&f)[U][NACC], int2 (&r)[U], int j) {
-#pragma unroll
-        for (int t = 0; t < U; ++t) r[t] = rec[j + t];
-#pragma unroll
-        for (int t = 0; t < U; ++t) {
-            const int row = (r[t].x >> kSubShift) * C + lane;
-#pragma unroll
-            for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
-        }
-    };
-    auto consume = [&](const float (&f)[U][NACC], const int2 (&r)[U], int count) {
-#pragma unroll
-        for (int t = 0; t < U; ++t) {
-            if (t < count) {                              // warp-uniform (compile-time true for full groups)
-                const int v = r[t].x & (kSub - 1);
-                if (v != cur_v) {                         // warp-uniform: a new interval starts
-                    if (cur_v >= 0) flush();
-#pragma unroll
-                    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-                    cur_v = v;
-                }
-                const float d = __int_as_float(r[t].y);
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d, acc[k]);
+        for (int g = 0; g < kRun; ++g) {
+            const int pa = __shfl_sync(0xffffffffu, my_pt, g), pb = __shfl_sync(0xffffffffu, my_pt, g + 1);
+            mx[g] = 0; mr[g] = -1;
+            if (g < nrun && pa + lane < pb) {
+                const int q = __ldg(a.rf + pa + lane);
+                const int v = __ldg(a.rb + pa + lane) - bV;      // sub-tiles start at multiples of 32 in a sample
+                mr[g] = __ldg(a.rd + pa + lane);
+                mx[g] = (q << kSubShift) | (v & (kSub - 1));
             }
         }
-    };
-
-    int2 mine = load_rec(pa);
-    for (int i0 = pa; i0 < pb; i0 += 32) {
-        const int n = min(32, pb - i0);
-        __syncwarp();
-        rec[lane] = mine;
-        if (lane < 8) rec[32 + lane] = make_int2(0, 0);
-        __syncwarp();
-        if (i0 + 32 < pb) mine = load_rec(i0 + 32);       // next batch's records fly during this batch
-        const int nfull = n & ~(U - 1);
-        float fa[U][NACC], fb[U][NACC];
-        int2 ra[U], rb2[U];
-        if (nfull) {
-            load_group(fa, ra, 0);
-            for (int j = 0; j < nfull; j += 2 * U) {
-                const bool has_b = j + U < nfull;
-                if (has_b) load_group(fb, rb2, j + U);
-                consume(fa, ra, U);
-                if (has_b) {
-                    if (j + 2 * U < nfull) load_group(fa, ra, j + 2 * U);
-                    consume(fb, rb2, U);
-                }
-            }
+        float md[kRun];
+#pragma unroll
+        for (int g = 0; g < kRun; ++g) md[g] = (mr[g] >= 0) ? __ldg(a.depth + mr[g]) : 0.f;
+#pragma unroll
+        for (int g = 0; g < kRun; ++g) {
+            s_rx[g][lane] = mx[g];
+            s_rd[g][lane] = md[g];
+            if (lane < 8) { s_rx[g][32 + lane] = 0; s_rd[g][32 + lane] = 0.f; }
         }
-        if (nfull < n) {                                  // remainder group: rows of padding records are row 0
-            load_group(fa, ra, nfull);
-            consume(fa, ra, n - nfull);
-        }
+        if (lane < 8) { s_rx[kRun][32 + lane] = 0; s_rd[kRun][32 + lane] = 0.f; }
     }
-    if (cur_v >= 0) flush();
     __syncwarp();
 
-    if (LAYOUT == FO_LAYOUT_BCZYX) {
-        if (vec_out) {
-            // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
-            // logical chunk stored at smem position `chunk` of row r is (chunk - r) & 7: it alternates
-            // between two values as r advances by 4.
-            const int ck0 = (chunk - riq) & 7, ck1 = ck0 ^ 4;
-            float *d0 = pl + 4 * ck0;
-            float *d1 = pl + 4 * V + 4 * ck1;
-            const unsigned sa = sbase + 16u * lane;       // row riq, position chunk
-            const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
-            if (EXACT) {
+#pragma unroll 1
+    for (int g = 0; g < nrun; ++g) {
+        const int pa = __shfl_sync(0xffffffffu, my_pt, g), pb = __shfl_sync(0xffffffffu, my_pt, g + 1);
+        const int v0 = (su0 + g) << kSubShift;
+        const int nv = min(kSub, (int)V - v0);
+        float *pl = a.out + ((int64_t)b * C + riq) * V + v0;     // row riq of this sub-tile's block
+
+        if (pa >= pb && vec_out) {                        // empty sub-tile: stream zeros, no staging
+            if (4 * chunk < nv) {
+                float *dst = pl + 4 * chunk;
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EXACT) {
 #pragma unroll
-                for (int i = 0; i < 4 * NACC; ++i) {
-                    const float4 x0 = lds_f4(sa + 1024u * i);
-                    const float4 x1 = lds_f4(sa + 1024u * i + 512u);
-                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
-                    if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
+                    for (int i = 0; i < 8 * NACC; ++i) __stcs(reinterpret_cast<float4 *>(dst + (4 * i) * V), zero4);
+                } else {
+                    for (int r = riq; r < C; r += 4, dst += 4 * V) __stcs(reinterpret_cast<float4 *>(dst), zero4);
+                }
+            }
+            continue;
+        }
+        if (EXACT) {
+#pragma unroll
+            for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
+        } else {
+            for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
+        }
+        const int *rx = s_rx[g];
+        const float *rdv = s_rd[g];
+
+        float acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+        int cur_v = -1;
+        auto flush = [&]() {
+            const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k)
+                if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
+        };
+        auto load_group = [&](float (&f)[U][NACC], int (&r)[U], int j) {
+#pragma unroll
+            for (int t = 0; t < U; ++t) r[t] = rx[j + t];
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+                const int row = (r[t] >> kSubShift) * C + lane;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
+            }
+        };
+        auto consume = [&](const float (&f)[U][NACC], const int (&r)[U], int j, int count) {
+            float d[U];
+#pragma unroll
+            for (int t = 0; t < U; ++t) d[t] = rdv[j + t];
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+                if (t < count) {                          // warp-uniform (compile-time true for full groups)
+                    const int v = r[t] & (kSub - 1);
+                    if (v != cur_v) {                     // warp-uniform: a new interval starts
+                        if (cur_v >= 0) flush();
+#pragma unroll
+                        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+                        cur_v = v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d[t], acc[k]);
+                }
+            }
+        };
+
+        int mx = 0, mr = -1;                              // records of the NEXT batch (sub-tiles > 32 points)
+        for (int i0 = pa; i0 < pb; i0 += 32) {
+            const int n = min(32, pb - i0);
+            const int nfull = n & ~(U - 1);
+            float fa[U][NACC], fb[U][NACC];
+            int ra[U], rb2[U];
+            load_group(fa, ra, 0);                        // rows of padding records are row 0
+            const bool more = i0 + 32 < pb;
+            if (more) {                                   // next batch's records fly during this batch
+                mx = 0; mr = -1;
+                if (i0 + 32 + lane < pb) {
+                    const int q = __ldg(a.rf + i0 + 32 + lane);
+                    const int v = __ldg(a.rb + i0 + 32 + lane) - bV;
+                    mr = __ldg(a.rd + i0 + 32 + lane);
+                    mx = (q << kSubShift) | (v & (kSub - 1));
+                }
+            }
+            float md = 0.f;
+            if (nfull) {
+                for (int j = 0; j < nfull; j += 2 * U) {
+                    const bool has_b = j + U < nfull;
+                    if (has_b) load_group(fb, rb2, j + U);
+                    consume(fa, ra, j, U);
+                    if (j == 0 && more) md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
+                    if (has_b) {
+                        if (j + 2 * U < nfull) load_group(fa, ra, j + 2 * U);
+                        consume(fb, rb2, j + U, U);
+                    }
+                }
+                if (nfull < n) {                          // remainder group
+                    load_group(fa, ra, nfull);
+                    consume(fa, ra, nfull, n - nfull);
                 }
             } else {
-                for (int r = riq, i = 0; r < C; r += 8, ++i) {
-                    const float4 x0 = lds_f4(sa + 1024u * i);
-                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
-                    if (r + 4 < C) {
+                consume(fa, ra, 0, n);
+            }
+            if (more) {
+                __syncwarp();
+                s_rx[kRun][lane] = mx;
+                s_rd[kRun][lane] = md;
+                __syncwarp();
+                rx = s_rx[kRun];
+                rdv = s_rd[kRun];
+            }
+        }
+        if (cur_v >= 0) flush();
+        __syncwarp();
+
+        if (LAYOUT == FO_LAYOUT_BCZYX) {
+            if (vec_out) {
+                // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
+                // logical chunk stored at smem position `chunk` of row r is (chunk - r) & 7: it alternates
+                // between two values as r advances by 4.
+                const int ck0 = (chunk - riq) & 7, ck1 = ck0 ^ 4;
+                float *d0 = pl + 4 * ck0;
+                float *d1 = pl + 4 * V + 4 * ck1;
+                const unsigned sa = sbase + 16u * lane;   // row riq, position chunk
+                const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
+                if (EXACT) {
+#pragma unroll
+                    for (int i = 0; i < 4 * NACC; ++i) {
+                        const float4 x0 = lds_f4(sa + 1024u * i);
                         const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                        if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
                         if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
                     }
+                } else {
+                    for (int r = riq, i = 0; r < C; r += 8, ++i) {
+                        const float4 x0 = lds_f4(sa + 1024u * i);
+                        if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
+                        if (r + 4 < C) {
+                            const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                            if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
+                        }
+                    }
+                }
+            } else {
+                float *plane0 = a.out + ((int64_t)b * C) * V + v0;
+                for (int e = lane; e < C * kSub; e += 32) {
+                    const int c = e >> kSubShift, v = e & (kSub - 1);
+                    if (v < nv) __stcs(plane0 + (int64_t)c * V + v, smem[stage_index(c, v)]);
                 }
             }
         } else {
-            float *plane0 = a.out + ((int64_t)b * C) * V + v0;
-            for (int e = lane; e < C * kSub; e += 32) {
-                const int c = e >> kSubShift, v = e & (kSub - 1);
-                if (v < nv) __stcs(plane0 + (int64_t)c * V + v, stage[stage_index(c, v)]);
+            // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
+            float *dst = a.out + ((int64_t)bV + v0) * C;
+            for (int e = lane; e < nv * C; e += 32) {
+                const int v = e / C, c = e - v * C;
+                __stcs(dst + e, smem[stage_index(c, v)]);
             }
         }
-    } else {
-        // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
-        float *dst = a.out + (int64_t)vbase * C;
-        for (int e = lane; e < nv * C; e += 32) {
-            const int v = e / C, c = e - v * C;
-            __stcs(dst + e, stage[stage_index(c, v)]);
-        }
+        __syncwarp();                                     // the stage is re-zeroed by the next sub-tile
     }
 }
 
@@ -285,7 +349,7 @@ template <int NACC, bool EXACT, int LAYOUT>
 int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(a.B, n_ctas), kThreads, smem, stream>>>(a);
+    kern<<<dim3(a.B, n_ctas), 32, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
     return FO_OK;
 }
@@ -336,10 +400,11 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = n_points; a.n_intervals = n_intervals; a.n_intervals_dev = n_intervals_dev;
     a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.sub_pt = pv.sub_pt;
+    a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
-    const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
+    const size_t smem = (size_t)kSub * c * sizeof(float);
     // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
-    const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;      // per sample (grid.y)
+    const int n_ctas = (sps + kRun - 1) / kRun;                      // per sample (grid.y)
     const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas <= 65535 && B <= 65535;
     if (dense_ok) {
         int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
@@ -375,5 +440,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
+    a.sps = 0; a.check_flags = 0;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }
