@@ -57,113 +57,96 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 // records, no shuffles), shared-memory addresses are precomputed 32-bit values, feature rows are
 // fetched in groups of U with the NEXT group already in flight while the current one is consumed
 // (2*U rows in flight per lane), and the next 32 records are fetched while a batch is processed.
-#ifndef FO_FWD_MIN_CTAS
-#define FO_FWD_MIN_CTAS 32          // <= 64 registers: 32 single-warp CTAs per SM
-#endif
 #ifndef FO_FWD_U
 #define FO_FWD_U 8
 #endif
-#ifndef FO_FWD_RUN
-#define FO_FWD_RUN 1
+#ifndef FO_FWD_WARPS
+#define FO_FWD_WARPS 1
 #endif
-constexpr int kRun = FO_FWD_RUN;     // consecutive sub-tiles of one sample per warp (<= 31)
+constexpr int kFwdWarps = FO_FWD_WARPS;     // warps (= sub-tiles) per CTA
+#ifndef FO_FWD_MIN_CTAS
+#define FO_FWD_MIN_CTAS (32 / kFwdWarps)          // <= 64 registers: 32 resident warps per SM
+#endif
 
-// A warp owns a run of kRun consecutive sub-tiles (kRun = 1 in the shipped build).  The dependent chain
-//     point range -> rank records -> depth -> feature rows
-// is walked with as few round trips as possible: the plan's flag word and the point range are independent
-// loads (sub-tiles per sample is a kernel argument), the three record arrays are fetched together, and for a
-// run the first three links are walked once for all its sub-tiles.
+// One warp reduces one sub-tile; the kFwdWarps warps of a CTA own kFwdWarps CONSECUTIVE sub-tiles and write
+// them out TOGETHER after one barrier, so that every store instruction covers kFwdWarps*128 contiguous bytes
+// of one channel plane.  Why (profiles/micro/store_pattern.cu, B200): single-warp CTAs writing 128 B per
+// plane reach 5.9 TB/s on this tensor, CTAs writing >= 512 B per plane 6.7-6.9 TB/s (cudaMemset: 7.0).
 //
-// Measured on a B200 (headline shape, batch 8, profiles/r01_summary.md "forward experiments"): this kernel
-// wants MANY SHORT-LIVED warps.  kRun = 1 / 2 / 4 / 8: 149 / 154 / 160 / 197 us; a persistent variant with a
-// 4-deep software pipeline across sub-tiles (work tickets): 185 us, 308 us on an all-empty grid; 21 instead
-// of 32 resident CTAs per SM: 159 -> 149 us; streaming (evict-first) stores 149 us vs 169 us for write-back,
-// .cg or .wt stores.  Everything that makes a warp hold its slot longer, or spreads the lines written at
-// one time over a wider address window, loses more DRAM write efficiency than the saved latency gains.
+// The dependent chain  point range -> rank records -> {depth, feature rows}  is walked with as few round
+// trips as possible: the plan's flag word and the point range are independent loads (sub-tiles per sample is
+// a kernel argument), the three record arrays are fetched together, the first group of feature rows is
+// requested before the depth values are needed.
 template <int NACC, bool EXACT, int LAYOUT>
-__global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
     constexpr int U = NACC <= 2 ? FO_FWD_U : 4;          // feature rows per group
-    extern __shared__ __align__(16) float smem[];        // stage [C][32]
-    __shared__ __align__(16) int s_rx[kRun + 1][32 + 8];     // (feature row << 5 | voxel slot) per point
-    __shared__ __align__(16) float s_rd[kRun + 1][32 + 8];   // depth value per point; row kRun: later batches
+    constexpr int W = kFwdWarps;
+    extern __shared__ __align__(16) float smem[];        // W stages [C][32]
+    __shared__ __align__(16) int s_rx[W][32 + 8];        // (feature row << 5 | voxel slot) per point
+    __shared__ __align__(16) float s_rd[W][32 + 8];      // depth value per point
+    __shared__ int s_state[W];                           // 0: sub-tile out of range, 1: empty, 2: staged
 
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = EXACT ? 32 * NACC : a.C;
-    // grid = (B, ceil(subs_per_sample / kRun)): x-fastest block order interleaves the samples, so the
+    // grid = (B, ceil(subs_per_sample / W)): x-fastest block order interleaves the samples, so the
     // dense near-ego regions of all samples are reached at the same relative time
     const int sps = a.sps;
     const int b = blockIdx.x;
-    const int su0 = blockIdx.y * kRun;
-    const int nrun = min(kRun, sps - su0);
-    // one round trip: the plan's flag word and the run's point ranges are independent loads
+    const int su = blockIdx.y * W + warp;
+    const bool in_range = su < sps;
+    // one round trip: the plan's flag word and the point range are independent loads
     const int flags = a.check_flags ? __ldg(&a.hdr->flags) : 0;
-    int my_pt = 0;
-    if (lane <= nrun) my_pt = __ldg(a.sub_pt + b * sps + su0 + lane);
-    if (flags & kFlagUnsorted) return;                   // the order-agnostic path runs instead
+    int pa = 0, pb = 0;
+    if (in_range) { pa = __ldg(a.sub_pt + b * sps + su); pb = __ldg(a.sub_pt + b * sps + su + 1); }
+    if (flags & kFlagUnsorted) return;                   // (uniform) the order-agnostic path runs instead
     const int64_t V = a.V;
     const int bV = b * (int)V;                           // global voxel id of the sample's first voxel (< 2^31)
+    const int v0 = su << kSubShift;
+    const int nv = in_range ? min(kSub, (int)V - v0) : 0;
     const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((V & 3) == 0);
     const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    float *stage = smem + warp * C * kSub;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
     const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
     const unsigned lane_rot = ((unsigned)lane & 7u) << 4;             // its rotation, in bytes
+    float *pl = a.out + ((int64_t)b * C + riq) * V + v0;             // row riq of this sub-tile's block
+    const bool staged = pa < pb || (in_range && !vec_out);
 
-    // ---- the run's first-batch records: everything in flight at once ----
-    {
-        int mx[kRun], mr[kRun];
+    if (W == 1 && !staged) {                              // empty sub-tile: stream zeros, no staging
+        if (4 * chunk < nv) {
+            float *dst = pl + 4 * chunk;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EXACT) {
 #pragma unroll
-        for (int g = 0; g < kRun; ++g) {
-            const int pa = __shfl_sync(0xffffffffu, my_pt, g), pb = __shfl_sync(0xffffffffu, my_pt, g + 1);
-            mx[g] = 0; mr[g] = -1;
-            if (g < nrun && pa + lane < pb) {
-                const int q = __ldg(a.rf + pa + lane);
-                const int v = __ldg(a.rb + pa + lane) - bV;      // sub-tiles start at multiples of 32 in a sample
-                mr[g] = __ldg(a.rd + pa + lane);
-                mx[g] = (q << kSubShift) | (v & (kSub - 1));
+                for (int i = 0; i < 8 * NACC; ++i) __stcs(reinterpret_cast<float4 *>(dst + (4 * i) * V), zero4);
+            } else {
+                for (int r = riq; r < C; r += 4, dst += 4 * V) __stcs(reinterpret_cast<float4 *>(dst), zero4);
             }
         }
-        float md[kRun];
-#pragma unroll
-        for (int g = 0; g < kRun; ++g) md[g] = (mr[g] >= 0) ? __ldg(a.depth + mr[g]) : 0.f;
-#pragma unroll
-        for (int g = 0; g < kRun; ++g) {
-            s_rx[g][lane] = mx[g];
-            s_rd[g][lane] = md[g];
-            if (lane < 8) { s_rx[g][32 + lane] = 0; s_rd[g][32 + lane] = 0.f; }
-        }
-        if (lane < 8) { s_rx[kRun][32 + lane] = 0; s_rd[kRun][32 + lane] = 0.f; }
+        return;
     }
-    __syncwarp();
+    if (W > 1 && lane == 0) s_state[warp] = !in_range ? 0 : (staged ? 2 : 1);
 
-#pragma unroll 1
-    for (int g = 0; g < nrun; ++g) {
-        const int pa = __shfl_sync(0xffffffffu, my_pt, g), pb = __shfl_sync(0xffffffffu, my_pt, g + 1);
-        const int v0 = (su0 + g) << kSubShift;
-        const int nv = min(kSub, (int)V - v0);
-        float *pl = a.out + ((int64_t)b * C + riq) * V + v0;     // row riq of this sub-tile's block
-
-        if (pa >= pb && vec_out) {                        // empty sub-tile: stream zeros, no staging
-            if (4 * chunk < nv) {
-                float *dst = pl + 4 * chunk;
-                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EXACT) {
-#pragma unroll
-                    for (int i = 0; i < 8 * NACC; ++i) __stcs(reinterpret_cast<float4 *>(dst + (4 * i) * V), zero4);
-                } else {
-                    for (int r = riq; r < C; r += 4, dst += 4 * V) __stcs(reinterpret_cast<float4 *>(dst), zero4);
-                }
+    if (staged) {
+        int *rx = s_rx[warp];
+        float *rdv = s_rd[warp];
+        int mx = 0, mr = -1;
+        auto load_idx = [&](int i0) {
+            mx = 0; mr = -1;
+            if (i0 + lane < pb) {
+                const int q = __ldg(a.rf + i0 + lane);
+                const int v = __ldg(a.rb + i0 + lane) - bV;      // sub-tiles start at multiples of 32 in a sample
+                mr = __ldg(a.rd + i0 + lane);
+                mx = (q << kSubShift) | (v & (kSub - 1));
             }
-            continue;
-        }
+        };
+        load_idx(pa);
         if (EXACT) {
 #pragma unroll
             for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
         } else {
             for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
         }
-        const int *rx = s_rx[g];
-        const float *rdv = s_rd[g];
-
         float acc[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
@@ -204,24 +187,21 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
             }
         };
 
-        int mx = 0, mr = -1;                              // records of the NEXT batch (sub-tiles > 32 points)
+        float md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
         for (int i0 = pa; i0 < pb; i0 += 32) {
             const int n = min(32, pb - i0);
+            __syncwarp();
+            rx[lane] = mx;
+            if (lane < 8) { rx[32 + lane] = 0; rdv[32 + lane] = 0.f; }
+            __syncwarp();
             const int nfull = n & ~(U - 1);
             float fa[U][NACC], fb[U][NACC];
             int ra[U], rb2[U];
             load_group(fa, ra, 0);                        // rows of padding records are row 0
+            rdv[lane] = md;
+            __syncwarp();
             const bool more = i0 + 32 < pb;
-            if (more) {                                   // next batch's records fly during this batch
-                mx = 0; mr = -1;
-                if (i0 + 32 + lane < pb) {
-                    const int q = __ldg(a.rf + i0 + 32 + lane);
-                    const int v = __ldg(a.rb + i0 + 32 + lane) - bV;
-                    mr = __ldg(a.rd + i0 + 32 + lane);
-                    mx = (q << kSubShift) | (v & (kSub - 1));
-                }
-            }
-            float md = 0.f;
+            if (more) load_idx(i0 + 32);                  // next batch's records fly during this batch
             if (nfull) {
                 for (int j = 0; j < nfull; j += 2 * U) {
                     const bool has_b = j + U < nfull;
@@ -240,62 +220,74 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
             } else {
                 consume(fa, ra, 0, n);
             }
-            if (more) {
-                __syncwarp();
-                s_rx[kRun][lane] = mx;
-                s_rd[kRun][lane] = md;
-                __syncwarp();
-                rx = s_rx[kRun];
-                rdv = s_rd[kRun];
-            }
         }
         if (cur_v >= 0) flush();
-        __syncwarp();
+    }
 
-        if (LAYOUT == FO_LAYOUT_BCZYX) {
-            if (vec_out) {
-                // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
-                // logical chunk stored at smem position `chunk` of row r is (chunk - r) & 7: it alternates
-                // between two values as r advances by 4.
-                const int ck0 = (chunk - riq) & 7, ck1 = ck0 ^ 4;
-                float *d0 = pl + 4 * ck0;
-                float *d1 = pl + 4 * V + 4 * ck1;
-                const unsigned sa = sbase + 16u * lane;   // row riq, position chunk
-                const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
-                if (EXACT) {
+    if (W > 1 && vec_out) {
+        // ---- cooperative write-out: one instruction = 4 consecutive sub-tiles x 128 B of ONE plane ----
+        __syncthreads();
+        const int sub = lane >> 3;                        // which of the 4 sub-tiles of a segment
+        for (int seg = 0; seg < W; seg += 4) {
+            const int w = seg + sub;
+            const int st = (w < W) ? s_state[w] : 0;
+            const int su_w = blockIdx.y * W + w;
+            const int nv_w = st ? min(kSub, (int)V - (su_w << kSubShift)) : 0;
+            const bool wr = 4 * chunk < nv_w;
+            const unsigned sw = (unsigned)__cvta_generic_to_shared(smem + w * C * kSub);
+            float *dst = a.out + (int64_t)b * C * V + ((int64_t)su_w << kSubShift) + 4 * chunk;
+            for (int c = warp; c < C; c += W) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (st == 2) x = lds_f4(sw + ((unsigned)c << 7) + ((unsigned)((chunk + c) & 7) << 4));
+                if (wr) __stcs(reinterpret_cast<float4 *>(dst + (int64_t)c * V), x);
+            }
+        }
+        return;
+    }
+    if (!staged) return;
+    __syncwarp();
+    if (LAYOUT == FO_LAYOUT_BCZYX) {
+        if (vec_out) {
+            // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
+            // logical chunk stored at smem position `chunk` of row r is (chunk - r) & 7: it alternates
+            // between two values as r advances by 4.
+            const int ck0 = (chunk - riq) & 7, ck1 = ck0 ^ 4;
+            float *d0 = pl + 4 * ck0;
+            float *d1 = pl + 4 * V + 4 * ck1;
+            const unsigned sa = sbase + 16u * lane;       // row riq, position chunk
+            const bool w0 = 4 * ck0 < nv, w1 = 4 * ck1 < nv;
+            if (EXACT) {
 #pragma unroll
-                    for (int i = 0; i < 4 * NACC; ++i) {
-                        const float4 x0 = lds_f4(sa + 1024u * i);
-                        const float4 x1 = lds_f4(sa + 1024u * i + 512u);
-                        if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
-                        if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
-                    }
-                } else {
-                    for (int r = riq, i = 0; r < C; r += 8, ++i) {
-                        const float4 x0 = lds_f4(sa + 1024u * i);
-                        if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
-                        if (r + 4 < C) {
-                            const float4 x1 = lds_f4(sa + 1024u * i + 512u);
-                            if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
-                        }
-                    }
+                for (int i = 0; i < 4 * NACC; ++i) {
+                    const float4 x0 = lds_f4(sa + 1024u * i);
+                    const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
+                    if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
                 }
             } else {
-                float *plane0 = a.out + ((int64_t)b * C) * V + v0;
-                for (int e = lane; e < C * kSub; e += 32) {
-                    const int c = e >> kSubShift, v = e & (kSub - 1);
-                    if (v < nv) __stcs(plane0 + (int64_t)c * V + v, smem[stage_index(c, v)]);
+                for (int r = riq, i = 0; r < C; r += 8, ++i) {
+                    const float4 x0 = lds_f4(sa + 1024u * i);
+                    if (w0) __stcs(reinterpret_cast<float4 *>(d0 + (8 * i) * V), x0);
+                    if (r + 4 < C) {
+                        const float4 x1 = lds_f4(sa + 1024u * i + 512u);
+                        if (w1) __stcs(reinterpret_cast<float4 *>(d1 + (8 * i) * V), x1);
+                    }
                 }
             }
         } else {
-            // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
-            float *dst = a.out + ((int64_t)bV + v0) * C;
-            for (int e = lane; e < nv * C; e += 32) {
-                const int v = e / C, c = e - v * C;
-                __stcs(dst + e, smem[stage_index(c, v)]);
+            float *plane0 = a.out + ((int64_t)b * C) * V + v0;
+            for (int e = lane; e < C * kSub; e += 32) {
+                const int c = e >> kSubShift, v = e & (kSub - 1);
+                if (v < nv) __stcs(plane0 + (int64_t)c * V + v, stage[stage_index(c, v)]);
             }
         }
-        __syncwarp();                                     // the stage is re-zeroed by the next sub-tile
+    } else {
+        // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
+        float *dst = a.out + ((int64_t)bV + v0) * C;
+        for (int e = lane; e < nv * C; e += 32) {
+            const int v = e / C, c = e - v * C;
+            __stcs(dst + e, stage[stage_index(c, v)]);
+        }
     }
 }
 
@@ -349,7 +341,7 @@ template <int NACC, bool EXACT, int LAYOUT>
 int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(a.B, n_ctas), 32, smem, stream>>>(a);
+    kern<<<dim3(a.B, n_ctas), 32 * kFwdWarps, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
     return FO_OK;
 }
@@ -402,9 +394,9 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.sub_pt = pv.sub_pt;
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
-    const size_t smem = (size_t)kSub * c * sizeof(float);
+    const size_t smem = (size_t)kFwdWarps * kSub * c * sizeof(float);
     // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
-    const int n_ctas = (sps + kRun - 1) / kRun;                      // per sample (grid.y)
+    const int n_ctas = (sps + kFwdWarps - 1) / kFwdWarps;            // per sample (grid.y)
     const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas <= 65535 && B <= 65535;
     if (dense_ok) {
         int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)

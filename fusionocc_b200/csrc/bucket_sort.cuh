@@ -68,6 +68,7 @@ struct ScanArgs {
     int32_t *iv_starts;      // compact outputs, one entry per non-empty bucket
     int32_t *iv_lengths;
     int32_t *iv_bucket;
+    int32_t *bucket2iv;      // optional [n_buckets]: interval id of every bucket (forward flavour: the plan's vox2iv)
     int32_t *totals;         // totals[0] = number of points, totals[1] = number of non-empty buckets
     // forward flavour: first interval / first point of every 32-voxel sub-tile (nullptr to skip)
     int32_t *sub_iv;
@@ -135,11 +136,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
     const bool want_tiles = a.sub_iv != nullptr;
     if (want_tiles) { sample = base / a.vox_per_sample; vin = base - sample * a.vox_per_sample; }
 
-    int o[kScanItems];
+    int o[kScanItems], iv[kScanItems];
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
         const int64_t v = base + j;
         o[j] = (int)pts;
+        iv[j] = (int)ne;
         if (v < a.n_buckets) {
             if (want_tiles) {
                 if ((vin & (kSub - 1)) == 0) {
@@ -162,10 +164,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
         int4 *dst = reinterpret_cast<int4 *>(a.cnt + base);
 #pragma unroll
         for (int j = 0; j < kScanItems / 4; ++j) dst[j] = make_int4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (a.bucket2iv) {
+            int4 *d2 = reinterpret_cast<int4 *>(a.bucket2iv + base);
+#pragma unroll
+            for (int j = 0; j < kScanItems / 4; ++j)
+                d2[j] = make_int4(iv[4 * j], iv[4 * j + 1], iv[4 * j + 2], iv[4 * j + 3]);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j)
-            if (base + j < a.n_buckets) a.cnt[base + j] = o[j];
+            if (base + j < a.n_buckets) {
+                a.cnt[base + j] = o[j];
+                if (a.bucket2iv) a.bucket2iv[base + j] = iv[j];
+            }
     }
     // the thread that owns the last bucket publishes the totals
     if (base <= a.n_buckets - 1 && a.n_buckets - 1 < base + kScanItems) {
@@ -178,19 +189,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
 }
 
 // ----------------------------------------------------------------------------------------------
-// In-segment ordering.  One lane per interval for the short ones (len <= 4: sorting network in
-// registers); longer intervals are handled one at a time by the whole warp: bitonic in registers for
-// len <= 32, in shared memory for len <= kSortSmem, in global memory (single warp, any length) above.
+// In-segment ordering.  One lane per interval for the short ones (len <= 8: sorting network in
+// registers); longer intervals are handled one at a time by a whole warp in registers (bitonic for
+// len <= 32, rank-by-counting for len <= 128) or by a whole CTA in shared memory (len <= kSortSmemCta);
+// beyond that (degenerate geometry) a single warp runs the network in global memory.
 // ----------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 128;
-constexpr int kSortSmem    = 1024;   // ints of shared memory per warp
+constexpr int kSortSmemCta = 4096;   // ints of shared memory per CTA: the longest interval sorted on chip
 
 __device__ __forceinline__ void cswap(int &a, int &b) {
     const int lo = min(a, b), hi = max(a, b);
     a = lo; b = hi;
 }
 
-__device__ inline void warp_sort_segment(int32_t *seg, int len, int *smem /* kSortSmem ints, per warp */, int lane) {
+__device__ inline void warp_sort_segment(int32_t *seg, int len, int * /*unused*/, int lane) {
     if (len <= 32) {
         int v = (lane < len) ? seg[lane] : INT_MAX;
 #pragma unroll
@@ -243,26 +255,6 @@ __device__ inline void warp_sort_segment(int32_t *seg, int len, int *smem /* kSo
     }
     int n2 = 256;
     while (n2 < len) n2 <<= 1;
-    if (n2 <= kSortSmem) {
-        for (int i = lane; i < n2; i += 32) smem[i] = (i < len) ? seg[i] : INT_MAX;
-        __syncwarp();
-        for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = lane; i < n2; i += 32) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const int a = smem[i], b = smem[l];
-                        const bool up = ((i & k) == 0);
-                        if ((a > b) == up) { smem[i] = b; smem[l] = a; }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        for (int i = lane; i < len; i += 32) seg[i] = smem[i];
-        __syncwarp();
-        return;
-    }
     // very long segment (degenerate geometry): sorting network directly in global memory.  This is the
     // "always ascending" bitonic form — the first stage of every merge pairs i with its mirror
     // i ^ (k-1), later stages with i ^ j — so every compare-exchange moves the minimum to the lower
@@ -293,14 +285,14 @@ struct OrderArgs {
     // forward flavour outputs (nullptr for the backward plan)
     int32_t *ranks_feat;
     int32_t *ranks_bev;
-    int32_t *pos2iv;
-    int32_t *pt2pos;            // frustum point -> sorted position (its -1 entries were written by voxelise)
     int32_t dhw, hw;            // D*H*W and H*W: ranks_feat = (p / dhw) * hw + p % hw  (view_transformer.py:239-244)
     // intervals longer than kLaneSortMax are queued here by the short pass and ordered, one warp each,
     // by the long pass — dense near-ego voxels are consecutive in voxel order, so without the queue a
     // few warps would inherit dozens of long intervals each (measured: 103 us -> tail-bound)
     int32_t *long_list;
-    int32_t *long_count;        // zero-initialised
+    int32_t *long_count;        // zero-initialised; [0] = intervals of kLaneSortMax+1 .. kWarpSortMax points,
+                                // [1] = longer ones, queued from the END of long_list (long_cap - 1 downwards)
+    int32_t long_cap;
 };
 
 // 19-comparator optimal sorting network for 8 keys (ascending)
@@ -315,6 +307,7 @@ __device__ __forceinline__ void sort8(int (&v)[8]) {
 }
 
 constexpr int kLaneSortMax = 8;   // intervals up to this length are ordered by one lane in registers
+constexpr int kWarpSortMax = 128; // ... up to this length by one warp in registers; longer ones by a whole CTA
 
 template <bool kForward>
 __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
@@ -323,9 +316,11 @@ __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         const int s = a.iv_starts[k], len = a.iv_lengths[k];
         if (len > kLaneSortMax) {
-            a.long_list[atomicAdd(a.long_count, 1)] = k;
+            if (len > kWarpSortMax) a.long_list[a.long_cap - 1 - atomicAdd(a.long_count + 1, 1)] = k;
+            else a.long_list[atomicAdd(a.long_count, 1)] = k;
             continue;
         }
+        if (!kForward && len == 1) continue;
         const int bucket = kForward ? a.iv_bucket[k] : 0;
         int v[8];
 #pragma unroll
@@ -338,36 +333,77 @@ __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
                 if (kForward) {
                     a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
                     a.ranks_bev[s + j] = bucket;
-                    a.pos2iv[s + j] = k;
-                    a.pt2pos[v[j]] = s + j;
                 }
             }
         }
     }
 }
 
+// CTA-wide bitonic sort of `len` distinct keys in shared memory (n2 = next power of two <= kSortSmemCta).
+__device__ inline void cta_sort_segment(int32_t *seg, int len, int *smem) {
+    int n2 = 256;
+    while (n2 < len) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += kSortThreads) smem[i] = (i < len) ? seg[i] : INT_MAX;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += kSortThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;      // the pair (i, i + j)
+                const int x = smem[i], y = smem[l];
+                const bool up = ((i & k) == 0);
+                if ((x > y) == up) { smem[i] = y; smem[l] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < len; i += kSortThreads) seg[i] = smem[i];
+    __syncthreads();
+}
+
 template <bool kForward>
 __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
-    __shared__ int s_sort[kSortThreads / 32][kSortSmem];
-    const int n = *a.long_count;
+    __shared__ int s_sort[kSortSmemCta];
+    const int n = a.long_count[0], n_big = a.long_count[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = gridDim.x * (kSortThreads / 32);
+    // (1) one warp per interval of up to kWarpSortMax points, all in registers
     for (int w = blockIdx.x * (kSortThreads / 32) + warp; w < n; w += nwarps) {
         const int k = a.long_list[w];
         const int ls = a.iv_starts[k], ll = a.iv_lengths[k];
         const int lb = kForward ? a.iv_bucket[k] : 0;
-        warp_sort_segment(a.sorted + ls, ll, s_sort[warp], lane);
+        warp_sort_segment(a.sorted + ls, ll, nullptr, lane);
         __syncwarp();
         if (kForward) {
             for (int j = lane; j < ll; j += 32) {
                 const int p = a.sorted[ls + j];
                 a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
                 a.ranks_bev[ls + j] = lb;
-                a.pos2iv[ls + j] = k;
-                a.pt2pos[p] = ls + j;
             }
         }
         __syncwarp();
+    }
+    if (n_big == 0) return;
+    // (2) one CTA per longer interval (a lone warp needs ~30 us for 256 keys: it was this kernel's tail)
+    __syncthreads();
+    for (int w = blockIdx.x; w < n_big; w += gridDim.x) {
+        const int k = a.long_list[a.long_cap - 1 - w];
+        const int ls = a.iv_starts[k], ll = a.iv_lengths[k];
+        const int lb = kForward ? a.iv_bucket[k] : 0;
+        if (ll <= kSortSmemCta) {
+            cta_sort_segment(a.sorted + ls, ll, s_sort);
+        } else {                                          // degenerate geometry: global-memory network, one warp
+            if (warp == 0) warp_sort_segment(a.sorted + ls, ll, nullptr, lane);
+            __threadfence_block();
+            __syncthreads();
+        }
+        if (kForward) {
+            for (int j = threadIdx.x; j < ll; j += kSortThreads) {
+                const int p = a.sorted[ls + j];
+                a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                a.ranks_bev[ls + j] = lb;
+            }
+        }
+        __syncthreads();
     }
 }
 

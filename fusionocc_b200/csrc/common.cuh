@@ -49,7 +49,7 @@ struct __align__(16) FwdPlanHeader {
     int32_t n_subs;          // number of sub-tiles = B * subs_per_sample
     int32_t subs_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
-    int32_t structured;      // 1: pt2pos is valid (plan produced by fo_rank_prepare)
+    int32_t structured;      // 1: pt2vox / vox2iv are valid (plan produced by fo_rank_prepare)
     int32_t reserved[11];
 };
 static_assert(sizeof(FwdPlanHeader) == 64, "header is one 64-byte block");
@@ -67,21 +67,26 @@ __host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vo
 
 // ----------------------------------------------------------------------------------------------
 // Forward plan buffer:
-//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | pos2iv[P_cap] | pt2pos[P_cap] | iv_vox[IV_cap]]
+//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | vox2iv[NV] | pos2iv[P_cap] | pt2vox[P_cap] | iv_vox[IV_cap]]
 //   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
 //   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
-//   pos2iv[i]     interval id of sorted position i (rows of the backward's gathered out_grad)
-//   pt2pos[p]     sorted position of frustum point p, -1 if filtered (only when hdr.structured)
+//   vox2iv[v]     interval id of voxel v (rows of the backward's gathered out_grad); only when hdr.structured
+//   pos2iv[i]     interval id of sorted position i; only for plans built from caller-supplied intervals
+//   pt2vox[p]     voxel id of frustum point p, -1 if filtered; only when hdr.structured
 //   iv_vox[k]     voxel id (= ranks_bev) of interval k
-//   P_cap = point capacity rounded up to 64, IV_cap = min(P_cap, B*Z*Y*X rounded up to 64).
+//   NV = B*Z*Y*X rounded up to 64, P_cap = point capacity rounded up to 64, IV_cap = min(P_cap, NV).
+// The structured arrays replace a point -> position -> interval chain: the order pass of the rank pipeline
+// then writes nothing but the three rank arrays (every scattered 4-byte access per point costs a 32-byte L2
+// sector, ~10 us per access per point at batch 8 — profiles/r01_summary.md).
 // ----------------------------------------------------------------------------------------------
 struct FwdPlanView {
     FwdPlanHeader *hdr;
     int32_t *sub_iv;
     int32_t *sub_pt;
+    int32_t *vox2iv;
     int32_t *pos2iv;
     int32_t *iv_vox;
-    int32_t *pt2pos;
+    int32_t *pt2vox;
     int64_t p_cap;           // point capacity of this buffer (multiple of 64)
     int64_t iv_cap;          // interval capacity
 };
@@ -91,14 +96,15 @@ __host__ inline size_t fwd_plan_sub_bytes(int64_t n_vox_total) {
 }
 __host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
     const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
-    return 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(8 * pc + 4 * (pc < nv ? pc : nv));
+    return 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv + 8 * pc + 4 * (pc < nv ? pc : nv));
 }
 // The layout is a pure function of (n_vox_total, plan_bytes): every entry point is handed the same
 // plan_bytes the buffer was sized with and recovers the same pointers without reading the device.
 __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_bytes, FwdPlanView *v) {
-    const size_t fixed = 256 + 2 * fwd_plan_sub_bytes(n_vox_total);
+    const int64_t nv = align_up(n_vox_total, 64);
+    const size_t fixed = 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv);
     if (plan_bytes < fixed + 64 * 12) return false;
-    const int64_t rest = (int64_t)(plan_bytes - fixed), nv = align_up(n_vox_total, 64);
+    const int64_t rest = (int64_t)(plan_bytes - fixed);
     int64_t pc = rest / 12;
     if (pc > nv) pc = (rest - 4 * nv) / 8;
     pc = pc / 64 * 64;
@@ -106,8 +112,9 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
     v->hdr = (FwdPlanHeader *)p;             p += 256;
     v->sub_iv = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->sub_pt = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
+    v->vox2iv = (int32_t *)p;                p += nv * 4;
     v->pos2iv = (int32_t *)p;                p += pc * 4;
-    v->pt2pos = (int32_t *)p;                p += pc * 4;
+    v->pt2vox = (int32_t *)p;                p += pc * 4;
     v->iv_vox = (int32_t *)p;
     v->p_cap = pc;
     v->iv_cap = pc < nv ? pc : nv;

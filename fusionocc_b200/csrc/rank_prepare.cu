@@ -21,7 +21,7 @@ struct VoxArgs {
     float lbx, lby, lbz, ivx, ivy, ivz;
     int32_t X, Y, Z;
     int32_t *cnt;                // [B*Z*Y*X] zero-initialised
-    int32_t *key;                // [n_points] voxel id or -1 (lives in the plan: becomes pt2pos)
+    int32_t *key;                // [n_points] voxel id or -1 (lives in the plan: pt2vox)
     int32_t *slot;               // [n_points]
     FwdPlanHeader *hdr;          // static fields initialised by thread 0
     int32_t n_subs, subs_per_sample;
@@ -161,13 +161,14 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
 // ------------------------------------------------------------------------------------------------
 // Backward plan, structured build (plans produced by fo_rank_prepare).
 // One warp per image pixel q = (b*N+n)*HW + hw: its <= D candidate points are p = ((b*N+n)*D + d)*HW + hw;
-// pt2pos gives each one's forward position (or -1).  The pixel's entries, in ascending forward
-// position (= ascending (ranks_bev, p): the order of bev_pool.py:47-49), are found by rank-by-counting
-// in registers — no sort passes, no atomics, fixed-stride rows of D entries.
+// pt2vox gives each one's voxel (or -1).  The forward order is (voxel id, point index) — a stable sort by
+// voxel — so the pixel's entries in ascending forward position (the order of bev_pool.py:47-49) are its
+// points sorted by (voxel id, depth bin d): no point -> position map is needed, and the gathered out_grad
+// row of a point is vox2iv[voxel].  No sort passes over memory, no atomics, fixed-stride rows of D entries.
 // ------------------------------------------------------------------------------------------------
-template <int R>   // R = ceil(D / 32) registers per lane
-__global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t *__restrict__ pt2pos,
-                                                                  const int32_t *__restrict__ pos2iv, int D, int HW,
+template <int R>   // R = ceil(D / 32) registers per lane; rank-by-counting on 64-bit (voxel, d) keys, D <= 256
+__global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t *__restrict__ pt2vox,
+                                                                  const int32_t *__restrict__ vox2iv, int D, int HW,
                                                                   int n_rows, BwdPlanHeader *hdr, int32_t *ent_p,
                                                                   int32_t *ent_iv, int32_t *starts, int32_t *lengths,
                                                                   int32_t *ids, const int32_t *n_points_dev) {
@@ -180,14 +181,14 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     }
     for (int q = warp0; q < n_rows; q += nwarps) {
         const int bn = q / HW, hw = q - bn * HW;
-        int pos[R];
+        long long key[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int d = lane + 32 * r;
-            pos[r] = INT_MAX;
+            key[r] = LLONG_MAX;
             if (d < D) {
-                const int v = __ldg(pt2pos + ((int64_t)bn * D + d) * HW + hw);
-                if (v >= 0) pos[r] = v;
+                const int v = __ldg(pt2vox + ((int64_t)bn * D + d) * HW + hw);
+                if (v >= 0) key[r] = ((long long)v << 8) | d;
             }
         }
         int rank[R];
@@ -197,18 +198,18 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
         for (int rr = 0; rr < R; ++rr) {
 #pragma unroll 8
             for (int l = 0; l < 32; ++l) {
-                const int other = __shfl_sync(0xffffffffu, pos[rr], l);
+                const long long other = __shfl_sync(0xffffffffu, key[rr], l);
 #pragma unroll
-                for (int r = 0; r < R; ++r) rank[r] += (other < pos[r]) ? 1 : 0;
+                for (int r = 0; r < R; ++r) rank[r] += (other < key[r]) ? 1 : 0;
             }
         }
         int cnt = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (pos[r] != INT_MAX) {
+            if (key[r] != LLONG_MAX) {
                 const int64_t e = (int64_t)q * D + rank[r];
                 ent_p[e] = (bn * D + lane + 32 * r) * HW + hw;
-                ent_iv[e] = __ldg(pos2iv + pos[r]);
+                ent_iv[e] = __ldg(vox2iv + (int)(key[r] >> 8));
                 ++cnt;
             }
         }
@@ -218,11 +219,11 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     }
 }
 
-// Same job with a bitonic network over packed keys (position << 7 | depth slot): 25 shuffle stages x R
-// registers instead of 32 x R broadcasts x R compares.  Needs positions < 2^24 (n_depth < 2^24) and D <= 128.
+// Same job with a bitonic network over packed 32-bit keys (voxel id << 7 | depth bin): 25 shuffle stages x R
+// registers instead of 32 x R broadcasts x R compares.  Needs B*Z*Y*X < 2^24 and D <= 128.
 template <int R>   // R in {1, 2, 4}: 32 * R >= D
 __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
-    const int32_t *__restrict__ pt2pos, const int32_t *__restrict__ pos2iv, int D, int HW, int n_rows,
+    const int32_t *__restrict__ pt2vox, const int32_t *__restrict__ vox2iv, int D, int HW, int n_rows,
     BwdPlanHeader *hdr, int32_t *ent_p, int32_t *ent_iv, int32_t *starts, int32_t *lengths, int32_t *ids,
     const int32_t *n_points_dev) {
     const int lane = threadIdx.x & 31;
@@ -238,10 +239,10 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
         int key[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int d = lane + 32 * r;                 // element index e = 32 r + lane holds depth slot d = e
+            const int d = lane + 32 * r;                 // element index e = 32 r + lane holds depth bin d = e
             key[r] = INT_MAX;
             if (d < D) {
-                const int v = __ldg(pt2pos + pbase + d * HW);
+                const int v = __ldg(pt2vox + pbase + d * HW);
                 if (v >= 0) key[r] = (v << 7) | d;
             }
         }
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
             if (key[r] != INT_MAX) {
                 const int e = 32 * r + lane;
                 ent_p[q * D + e] = pbase + (key[r] & 127) * HW;
-                ent_iv[q * D + e] = __ldg(pos2iv + (key[r] >> 7));
+                ent_iv[q * D + e] = __ldg(vox2iv + (key[r] >> 7));
                 ++cnt;
             }
         }
@@ -412,7 +413,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
 
     SortScratch ss = sort_scratch_view(scratch, NV);
     int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
-    int32_t *key = pv.pt2pos;                    // voxel id / -1 now, sorted position / -1 after the order pass
+    int32_t *key = pv.pt2vox;                    // voxel id of every frustum point, -1 if outside the grid
 
     FO_CUDA(cudaMemsetAsync(scratch, 0, ss.zero_bytes, stream));
     FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
@@ -430,6 +431,7 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     ScanArgs sa;
     sa.cnt = ss.cnt; sa.n_buckets = NV;
     sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = pv.iv_vox;
+    sa.bucket2iv = pv.vox2iv;
     sa.totals = counts_dev;
     sa.sub_iv = pv.sub_iv; sa.sub_pt = pv.sub_pt; sa.vox_per_sample = n_vox; sa.subs_per_sample = sps;
     sa.n_subs = (int)n_subs;
@@ -447,9 +449,10 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     OrderArgs oa;
     oa.sorted = ranks_depth; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
-    oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev; oa.pos2iv = pv.pos2iv; oa.pt2pos = pv.pt2pos;
+    oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev;
     oa.dhw = D * H * W; oa.hw = H * W;
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
+    oa.long_cap = (int32_t)P;
     const int64_t cap_iv = P < NV ? P : NV;
     order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<fwd>");
@@ -488,9 +491,9 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
         const int R = (D + 31) / 32;
         if (R > 8) return set_error(FO_ERR_UNSUPPORTED, "structured backward plan supports D <= 256 (got %d)", D);
         const int blocks = grid_for(n_feat_rows * 32, 256, 8);
-        if (D <= 128 && n_depth < (1 << 24)) {          // packed-key bitonic variant
+        if (D <= 128 && (int64_t)B * n_vox < (1 << 24)) {   // packed-key bitonic variant
 #define FO_BITONIC(RR)                                                                                          \
-    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2pos, fv.pos2iv, D, hw,             \
+    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2vox, fv.vox2iv, D, hw,             \
                                                                       (int)n_feat_rows, bv.hdr, bv.ent_p,      \
                                                                       bv.ent_iv, bv.starts, bv.lengths, bv.ids, \
                                                                       n_points_dev)
@@ -502,7 +505,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
             return FO_OK;
         }
 #define FO_STRUCT(RR)                                                                                         \
-    bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2pos, fv.pos2iv, D, hw, (int)n_feat_rows, \
+    bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2vox, fv.vox2iv, D, hw, (int)n_feat_rows, \
                                                               bv.hdr, bv.ent_p, bv.ent_iv, bv.starts,        \
                                                               bv.lengths, bv.ids, n_points_dev)
         switch (R) {
@@ -531,6 +534,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     ScanArgs sa;
     sa.cnt = ss.cnt; sa.n_buckets = n_feat_rows;
     sa.iv_starts = bv.starts; sa.iv_lengths = bv.lengths; sa.iv_bucket = bv.ids;
+    sa.bucket2iv = nullptr;
     sa.totals = bv.hdr->totals;
     sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = bv.hdr;
@@ -546,8 +550,8 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     OrderArgs oa;
     oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
     oa.n_intervals = &bv.hdr->n_bwd_intervals;
-    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.pos2iv = nullptr; oa.pt2pos = nullptr; oa.dhw = 1; oa.hw = 1;
-    oa.long_list = bv.slot; oa.long_count = ss.counter;
+    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.dhw = 1; oa.hw = 1;
+    oa.long_list = bv.slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)bv.cap;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<bwd>");
     order_long_kernel<false><<<148 * 16, kSortThreads, 0, stream>>>(oa);
