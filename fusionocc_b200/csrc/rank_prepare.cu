@@ -35,7 +35,56 @@ __device__ __forceinline__ int voxel_key(float x, float y, float z, int64_t b, c
     return kept ? (int)(((b * a.Z + iz) * a.Y + iy) * a.X + ix) : -1;
 }
 
-__global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
+// Fused geometry: the frustum point is computed from the calibration instead of being
+// read from a (B,N,D,H,W,3) tensor — view_transformer.py:161-172 per point:
+//     p = frustum - post_trans;  p = inv(post_rots) p;  p = (x z, y z, z);  p = (R_s2e inv(K)) p + t_s2e;  p = bda p
+// The four small matrices per camera are inputs (computed by the caller with the reference's own torch ops, so
+// their bits are the reference's); the per-point arithmetic is three 3x3 matrix-vector products whose fp32
+// summation order is chosen by `mode` (the reference runs them through a batched library GEMM):
+//   0: k-ascending FMA chain  fma(m2,z, fma(m1,y, m0*x))     1: separate multiplies and adds, k-ascending
+//   2: k-descending FMA chain fma(m0,x, fma(m1,y, m2*z))     3: fma(m1,y, m0*x) + m2*z
+// Mode 3 is what torch 2.11 / cuBLAS 12.8 executes for these broadcast 3x3 @ 3x1 products on a B200 (measured
+// by profiles/matmul_order_probe.py against an fp64 emulation of eleven candidate orders: 0 of 2 230 272
+// floats differ for mode 3, 15-42 % for every other order).
+struct CalibArgs {
+    const float *frustum;        // [D*H*W, 3]  (x_px, y_px, depth)                 view_transformer.py:105-133
+    const float *cam;            // [B*N, 24]   inv(post_rots) 9 | post_trans 3 | combine 9 | t_s2e 3
+    const float *bda;            // [B, 12]     bda 3x3 | translation 3 (zeros for a 3x3 bda)
+    int32_t n_cams, dhw, mode, bda_has_t;
+    float *coor_out;             // optional [n_points, 3]
+};
+
+__device__ __forceinline__ float dot3(int mode, float m0, float m1, float m2, float x, float y, float z) {
+    if (mode == 0) return fmaf(m2, z, fmaf(m1, y, __fmul_rn(m0, x)));
+    if (mode == 1) return __fadd_rn(__fadd_rn(__fmul_rn(m0, x), __fmul_rn(m1, y)), __fmul_rn(m2, z));
+    if (mode == 2) return fmaf(m0, x, fmaf(m1, y, __fmul_rn(m2, z)));
+    return __fadd_rn(fmaf(m1, y, __fmul_rn(m0, x)), __fmul_rn(m2, z));
+}
+
+__device__ __forceinline__ void calib_point(const CalibArgs &g, int p, float &ox, float &oy, float &oz) {
+    const int bn = p / g.dhw, r = p - bn * g.dhw;
+    const float *f = g.frustum + 3 * r;
+    const float *m = g.cam + 24 * bn;
+    const float *bd = g.bda + 12 * (bn / g.n_cams);
+    const float x0 = __fsub_rn(__ldg(f), __ldg(m + 9)), y0 = __fsub_rn(__ldg(f + 1), __ldg(m + 10)),
+                z0 = __fsub_rn(__ldg(f + 2), __ldg(m + 11));
+    const float x1 = dot3(g.mode, __ldg(m), __ldg(m + 1), __ldg(m + 2), x0, y0, z0);
+    const float y1 = dot3(g.mode, __ldg(m + 3), __ldg(m + 4), __ldg(m + 5), x0, y0, z0);
+    const float z1 = dot3(g.mode, __ldg(m + 6), __ldg(m + 7), __ldg(m + 8), x0, y0, z0);
+    const float x2 = __fmul_rn(x1, z1), y2 = __fmul_rn(y1, z1);
+    const float x3 = __fadd_rn(dot3(g.mode, __ldg(m + 12), __ldg(m + 13), __ldg(m + 14), x2, y2, z1), __ldg(m + 21));
+    const float y3 = __fadd_rn(dot3(g.mode, __ldg(m + 15), __ldg(m + 16), __ldg(m + 17), x2, y2, z1), __ldg(m + 22));
+    const float z3 = __fadd_rn(dot3(g.mode, __ldg(m + 18), __ldg(m + 19), __ldg(m + 20), x2, y2, z1), __ldg(m + 23));
+    ox = dot3(g.mode, __ldg(bd), __ldg(bd + 1), __ldg(bd + 2), x3, y3, z3);
+    oy = dot3(g.mode, __ldg(bd + 3), __ldg(bd + 4), __ldg(bd + 5), x3, y3, z3);
+    oz = dot3(g.mode, __ldg(bd + 6), __ldg(bd + 7), __ldg(bd + 8), x3, y3, z3);
+    if (g.bda_has_t) {
+        ox = __fadd_rn(ox, __ldg(bd + 9)); oy = __fadd_rn(oy, __ldg(bd + 10)); oz = __fadd_rn(oz, __ldg(bd + 11));
+    }
+}
+
+template <bool CALIB>
+__global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a, CalibArgs g) {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid == 0) {
         a.hdr->flags = 0;
@@ -46,14 +95,26 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_quads = a.n_points >> 2;
     for (int64_t qd = gtid; qd < n_quads; qd += stride) {
-        const float4 *src = reinterpret_cast<const float4 *>(a.coor) + qd * 3;
-        const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1), v2 = __ldcs(src + 2);
-        const float xs[4] = {v0.x, v0.w, v1.z, v2.y};
-        const float ys[4] = {v0.y, v1.x, v1.w, v2.z};
-        const float zs[4] = {v0.z, v1.y, v2.x, v2.w};
-        int keys[4], slots[4];
+        float xs[4], ys[4], zs[4];
         // n_points < 2^31 is enforced by the host wrapper: 32-bit index arithmetic
         const int p0 = (int)(qd << 2), pps = (int)a.points_per_sample;
+        if (CALIB) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) calib_point(g, p0 + j, xs[j], ys[j], zs[j]);
+            if (g.coor_out) {
+                float4 *dst = reinterpret_cast<float4 *>(g.coor_out) + qd * 3;
+                dst[0] = make_float4(xs[0], ys[0], zs[0], xs[1]);
+                dst[1] = make_float4(ys[1], zs[1], xs[2], ys[2]);
+                dst[2] = make_float4(zs[2], xs[3], ys[3], zs[3]);
+            }
+        } else {
+            const float4 *src = reinterpret_cast<const float4 *>(a.coor) + qd * 3;
+            const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1), v2 = __ldcs(src + 2);
+            xs[0] = v0.x; xs[1] = v0.w; xs[2] = v1.z; xs[3] = v2.y;
+            ys[0] = v0.y; ys[1] = v1.x; ys[2] = v1.w; ys[3] = v2.z;
+            zs[0] = v0.z; zs[1] = v1.y; zs[2] = v2.x; zs[3] = v2.w;
+        }
+        int keys[4], slots[4];
         const int b0 = p0 / pps, rem = p0 - b0 * pps;
 #pragma unroll
         for (int j = 0; j < 4; ++j) keys[j] = voxel_key(xs[j], ys[j], zs[j], b0 + (rem + j) / pps, a);
@@ -64,7 +125,14 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a) {
     }
     // tail (n_points % 4)
     for (int64_t p = (n_quads << 2) + gtid; p < a.n_points; p += stride) {
-        const int k = voxel_key(a.coor[3 * p], a.coor[3 * p + 1], a.coor[3 * p + 2], p / a.points_per_sample, a);
+        float x, y, z;
+        if (CALIB) {
+            calib_point(g, (int)p, x, y, z);
+            if (g.coor_out) { g.coor_out[3 * p] = x; g.coor_out[3 * p + 1] = y; g.coor_out[3 * p + 2] = z; }
+        } else {
+            x = a.coor[3 * p]; y = a.coor[3 * p + 1]; z = a.coor[3 * p + 2];
+        }
+        const int k = voxel_key(x, y, z, p / a.points_per_sample, a);
         a.key[p] = k;
         a.slot[p] = k >= 0 ? atomicAdd(a.cnt + k, 1) : 0;
     }
@@ -386,19 +454,18 @@ extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t 
     return bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256);
 }
 
-extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B, int32_t N, int32_t D, int32_t H,
-                               int32_t W, const float lower_bound[3], const float interval[3], int32_t X, int32_t Y,
-                               int32_t Z, int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
-                               int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev,
-                               void *fwd_plan, size_t fwd_plan_bytes, void *scratch, size_t scratch_bytes) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *calib, int32_t B, int32_t N, int32_t D,
+                      int32_t H, int32_t W, const float lower_bound[3], const float interval[3], int32_t X,
+                      int32_t Y, int32_t Z, int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
+                      int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev, void *fwd_plan,
+                      size_t fwd_plan_bytes, void *scratch, size_t scratch_bytes) {
     FO_CHECK_ARG(B >= 1 && N >= 1 && D >= 1 && H >= 1 && W >= 1, "non-positive frustum dims");
     FO_CHECK_ARG(X >= 1 && Y >= 1 && Z >= 1, "non-positive grid dims");
-    FO_CHECK_ARG(coor && lower_bound && interval, "NULL geometry input");
+    FO_CHECK_ARG(lower_bound && interval, "NULL grid description");
     FO_CHECK_ARG(ranks_bev && ranks_depth && ranks_feat && interval_starts && interval_lengths && counts_dev,
                  "NULL output array");
     FO_CHECK_ARG(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "scratch must be non-NULL, 256-byte aligned");
-    FO_CHECK_ARG(((uintptr_t)coor & 15) == 0, "coor must be 16-byte aligned");
     const int64_t pps = (int64_t)N * D * H * W;
     const int64_t P = pps * B;
     const int64_t n_vox = (int64_t)X * Y * Z;
@@ -425,7 +492,8 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     va.X = X; va.Y = Y; va.Z = Z;
     va.cnt = ss.cnt; va.key = key; va.slot = slot;
     va.hdr = pv.hdr; va.n_subs = (int)n_subs; va.subs_per_sample = sps;
-    voxelize_count_kernel<<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va);
+    if (calib) voxelize_count_kernel<true><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, *calib);
+    else voxelize_count_kernel<false><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, CalibArgs{});
     FO_LAUNCH_CHECK("voxelize_count_kernel");
 
     ScanArgs sa;
@@ -459,6 +527,38 @@ extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B
     order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<fwd>");
     return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_rank_prepare(fo_stream_t stream_, const float *coor, int32_t B, int32_t N, int32_t D, int32_t H,
+                               int32_t W, const float lower_bound[3], const float interval[3], int32_t X, int32_t Y,
+                               int32_t Z, int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
+                               int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev,
+                               void *fwd_plan, size_t fwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    FO_CHECK_ARG(coor != nullptr && ((uintptr_t)coor & 15) == 0, "coor must be non-NULL and 16-byte aligned");
+    return rank_prepare_impl((cudaStream_t)stream_, coor, nullptr, B, N, D, H, W, lower_bound, interval, X, Y, Z,
+                             ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, counts_dev,
+                             fwd_plan, fwd_plan_bytes, scratch, scratch_bytes);
+}
+
+extern "C" int fo_rank_prepare_calib(fo_stream_t stream_, const float *frustum, const float *cam_mats,
+                                     const float *bda, int32_t bda_has_translation, int32_t matvec_mode,
+                                     float *coor_out, int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+                                     const float lower_bound[3], const float interval[3], int32_t X, int32_t Y,
+                                     int32_t Z, int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
+                                     int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev,
+                                     void *fwd_plan, size_t fwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    FO_CHECK_ARG(frustum && cam_mats && bda, "NULL calibration input");
+    FO_CHECK_ARG(matvec_mode >= 0 && matvec_mode <= 3, "unknown matvec_mode %d", matvec_mode);
+    FO_CHECK_ARG(coor_out == nullptr || ((uintptr_t)coor_out & 15) == 0, "coor_out must be 16-byte aligned");
+    FO_CHECK_ARG(B >= 1 && N >= 1 && D >= 1 && H >= 1 && W >= 1, "non-positive frustum dims");
+    CalibArgs g;
+    g.frustum = frustum; g.cam = cam_mats; g.bda = bda;
+    g.n_cams = N; g.dhw = D * H * W; g.mode = matvec_mode; g.bda_has_t = bda_has_translation ? 1 : 0;
+    g.coor_out = coor_out;
+    return rank_prepare_impl((cudaStream_t)stream_, nullptr, &g, B, N, D, H, W, lower_bound, interval, X, Y, Z,
+                             ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, counts_dev,
+                             fwd_plan, fwd_plan_bytes, scratch, scratch_bytes);
 }
 
 extern "C" size_t fo_bwd_plan_bytes(int64_t n_points_capacity, int64_t n_feat_rows) {

@@ -38,7 +38,7 @@ try:  # optional mm* integration
 except Exception:  # noqa: BLE001
     _Base = nn.Module
 
-__all__ = ['LSSViewTransformer', 'rank_prepare']
+__all__ = ['LSSViewTransformer', 'rank_prepare', 'rank_prepare_calib', 'pack_calibration']
 
 
 def rank_prepare(coor: torch.Tensor, grid_lower_bound, grid_interval, grid_size_xyz
@@ -83,17 +83,85 @@ def rank_prepare(coor: torch.Tensor, grid_lower_bound, grid_interval, grid_size_
     return ranks_bev, ranks_depth, ranks_feat, starts, lengths, counts, plan
 
 
+def pack_calibration(sensor2ego, cam2imgs, post_rots, post_trans, bda):
+    """The per-camera matrices of get_lidar_coor (view_transformer.py:161-172) in the layout
+    fo_rank_prepare_calib reads: ``cam_mats`` (B*N, 24) = inv(post_rots) | post_trans | combine | t_s2e and
+    ``bda12`` (B, 12) = bda[:3,:3] | translation.  The two small products (``torch.inverse`` and
+    ``sensor2ego[:3,:3] @ inv(cam2img)``) are the reference's own torch ops on its own operands, so the
+    matrices carry the reference's bits; only the per-point products move into the kernel."""
+    B, N = sensor2ego.shape[:2]
+    f = lambda t: t.float()
+    inv_pr = torch.inverse(f(post_rots))
+    combine = f(sensor2ego)[:, :, :3, :3].matmul(torch.inverse(f(cam2imgs)[:, :, :3, :3]))
+    cam = torch.cat((inv_pr.reshape(B, N, 9), f(post_trans).reshape(B, N, 3), combine.reshape(B, N, 9),
+                     f(sensor2ego)[:, :, :3, 3].reshape(B, N, 3)), dim=2).reshape(B * N, 24).contiguous()
+    has_t = bda.shape[-1] == 4
+    t = f(bda)[:, :3, 3] if has_t else torch.zeros(B, 3, device=bda.device)
+    bda12 = torch.cat((f(bda)[:, :3, :3].reshape(B, 9), t), dim=1).contiguous()
+    return cam, bda12, has_t
+
+
+# fp32 summation order of the per-point 3x3 products that reproduces the reference's library GEMM on a B200
+# (measured by tests/test_gpu_fused_geometry.py; see fo_rank_prepare_calib in include/fusionocc_b200.h)
+DEFAULT_MATVEC_MODE = 3
+
+
+def rank_prepare_calib(frustum: torch.Tensor, cam_mats: torch.Tensor, bda12: torch.Tensor, bda_has_t: bool,
+                       B: int, N: int, grid_lower_bound, grid_interval, grid_size_xyz,
+                       matvec_mode: int = DEFAULT_MATVEC_MODE, return_coor: bool = False):
+    """Rank precompute with the geometry fused in (fo_rank_prepare_calib): same returns as
+    :func:`rank_prepare` (+ the materialised points when ``return_coor``).  No host sync."""
+    if not cam_mats.is_cuda:
+        raise RuntimeError('fusionocc_b200 rank precompute runs on CUDA tensors only (no CPU fallback)')
+    lib = _cabi.load()
+    D, H, W, three = frustum.shape
+    assert three == 3 and cam_mats.shape == (B * N, 24) and bda12.shape == (B, 12)
+    dev = cam_mats.device
+    frustum = frustum.to(device=dev, dtype=torch.float32).contiguous()
+    X, Y, Z = (int(v) for v in grid_size_xyz)
+    P = B * N * D * H * W
+    NV = B * X * Y * Z
+    cap_iv = min(P, NV)
+    i32 = dict(dtype=torch.int32, device=dev)
+    ranks_bev = torch.empty(P, **i32)
+    ranks_depth = torch.empty(P, **i32)
+    ranks_feat = torch.empty(P, **i32)
+    starts = torch.empty(cap_iv, **i32)
+    lengths = torch.empty(cap_iv, **i32)
+    counts = torch.empty(4, **i32)
+    coor = torch.empty(B, N, D, H, W, 3, device=dev) if return_coor else None
+    plan_bytes = lib.fo_fwd_plan_bytes(NV, P)
+    plan_buf = torch.empty(plan_bytes, dtype=torch.uint8, device=dev)
+    sbytes = lib.fo_rank_prepare_scratch_bytes(P, NV)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_rank_prepare_calib(
+            _stream(dev), _p(frustum), _p(cam_mats), _p(bda12), int(bda_has_t), int(matvec_mode), _p(coor),
+            B, N, D, H, W, _cabi.f3(grid_lower_bound), _cabi.f3(grid_interval), X, Y, Z,
+            _p(ranks_bev), _p(ranks_depth), _p(ranks_feat), _p(starts), _p(lengths), _p(counts),
+            _p(plan_buf), plan_bytes, _p(scratch), sbytes), 'fo_rank_prepare_calib')
+    plan = VoxelPoolPlan(plan_buf, B, X * Y * Z, P, cap_iv, counts_dev=counts)
+    plan.trusted = True
+    plan.structured_hw, plan.n_depth = H * W, P
+    out = (ranks_bev, ranks_depth, ranks_feat, starts, lengths, counts, plan)
+    return out + (coor,) if return_coor else out
+
+
 class LSSViewTransformer(_Base):
     r"""Lift-Splat-Shoot view transformer with BEVPoolv2 (https://arxiv.org/abs/2008.05711,
     https://arxiv.org/abs/2211.17111).  Arguments as in the reference (view_transformer.py:61-85).
 
-    Extra, opt-in argument: ``sync_free`` (default False) — ``voxel_pooling_v2`` skips the one
-    remaining host read-back; the all-filtered case then returns regular zeros of the normal output
-    shape instead of the reference's ``print`` + Z-collapsed dummy (:200-210).
+    Extra, opt-in arguments:
+    ``sync_free`` (default False) — ``voxel_pooling_v2`` skips the one remaining host read-back; the
+    all-filtered case then returns regular zeros of the normal output shape instead of the reference's
+    ``print`` + Z-collapsed dummy (:200-210).
+    ``fuse_geometry`` (default False) — the non-accelerated ``view_transform`` never materialises the
+    (B,N,D,H,W,3) frustum points: ``get_lidar_coor`` + ``voxel_pooling_prepare_v2`` run as ONE native call
+    (fo_rank_prepare_calib).  Implies the sync-free output contract.
     """
 
     def __init__(self, grid_config, input_size, downsample=16, in_channels=512, out_channels=64,
-                 accelerate=False, sid=False, collapse_z=True, sync_free=False):
+                 accelerate=False, sid=False, collapse_z=True, sync_free=False, fuse_geometry=False):
         super().__init__()
         self.grid_config = grid_config
         self.downsample = downsample
@@ -107,6 +175,7 @@ class LSSViewTransformer(_Base):
         self.initial_flag = True
         self.collapse_z = collapse_z
         self.sync_free = sync_free
+        self.fuse_geometry = fuse_geometry
         self._accel_plan: Optional[VoxelPoolPlan] = None
 
     # ------------------------------------------------------------------ a1 (:87-103)
@@ -234,11 +303,30 @@ class LSSViewTransformer(_Base):
             bev_feat = bev_pool_v2(depth, feat, self.ranks_depth, self.ranks_feat, self.ranks_bev,
                                    bev_feat_shape, self.interval_starts, self.interval_lengths)
             bev_feat = bev_feat.squeeze(2)
+        elif self.fuse_geometry:
+            bev_feat = self.voxel_pooling_fused(input[1:7], depth.view(B, N, self.D, H, W),
+                                                tran_feat.view(B, N, self.out_channels, H, W))
         else:
             coor = self.get_lidar_coor(*input[1:7])
             bev_feat = self.voxel_pooling_v2(coor, depth.view(B, N, self.D, H, W),
                                              tran_feat.view(B, N, self.out_channels, H, W))
         return bev_feat, depth
+
+    def voxel_pooling_fused(self, calib, depth, feat):
+        """get_lidar_coor + voxel_pooling_v2 (:135-173, :196-221) without the frustum-point tensor."""
+        sensor2ego, _ego2global, cam2imgs, post_rots, post_trans, bda = calib
+        B, N = sensor2ego.shape[:2]
+        X, Y, Z = self._grid_xyz()
+        cam, bda12, has_t = pack_calibration(sensor2ego, cam2imgs, post_rots, post_trans, bda)
+        rb, rd, rf, st, ln, counts, plan = rank_prepare_calib(
+            self._frustum_on(sensor2ego), cam, bda12, has_t, B, N, self.grid_lower_bound.tolist(),
+            self.grid_interval.tolist(), (X, Y, Z))
+        feat = feat.permute(0, 1, 3, 4, 2)
+        bev_feat_shape = (depth.shape[0], Z, Y, X, feat.shape[-1])
+        bev_feat = bev_pool_v2_with_plan(depth, feat, rd, rf, rb, bev_feat_shape, st, ln, plan)
+        if self.collapse_z:
+            bev_feat = torch.cat(bev_feat.unbind(dim=2), 1)
+        return bev_feat
 
     def view_transform(self, input, depth, tran_feat):
         if self.accelerate:

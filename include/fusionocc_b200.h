@@ -185,6 +185,35 @@ int fo_rank_prepare(fo_stream_t stream, const float *coor,
                     void *scratch, size_t scratch_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * Rank precompute with the geometry fused in.  Replaces view_transformer.py:135-173
+ * (get_lidar_coor: ~15 eager launches and 4-6 full-size (B,N,D,H,W,3) temporaries) AND :223-281: the
+ * frustum point is computed per thread from the calibration and never stored (unless coor_out != NULL).
+ *
+ *   frustum      fp32 [D*H*W, 3]   the (x_px, y_px, depth) template of create_frustum (:105-133)
+ *   cam_mats     fp32 [B*N, 24]    per camera: inv(post_rots) 3x3 row-major | post_trans 3 |
+ *                                  combine = sensor2ego[:3,:3] @ inv(cam2img) 3x3 | sensor2ego[:3,3]
+ *                                  (the caller forms the two small products with the reference's own ops)
+ *   bda          fp32 [B, 12]      bda 3x3 row-major | translation 3 (STCOcc's 4x4 bda; zeros otherwise)
+ *   matvec_mode  fp32 summation order of the three per-point 3x3 products: 0 = FMA chain k = 0,1,2;
+ *                1 = separate multiplies and adds; 2 = FMA chain k = 2,1,0; 3 = fma(m1,y, m0*x) + m2*z.
+ *                The reference runs them through a batched library GEMM; mode 3 reproduces its bits on a
+ *                B200 with torch 2.11 / CUDA 12.8 (tests/test_gpu_fused_geometry.py checks that, and
+ *                measures the voxel-index mismatch rate of the other orders).
+ *   coor_out     optional fp32 [B*N*D*H*W, 3]: also materialise the points (debug / parity tests)
+ * Everything else as fo_rank_prepare.
+ * ------------------------------------------------------------------------------------------------ */
+int fo_rank_prepare_calib(fo_stream_t stream, const float *frustum, const float *cam_mats, const float *bda,
+                          int32_t bda_has_translation, int32_t matvec_mode, float *coor_out,
+                          int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+                          const float lower_bound[3], const float interval[3],
+                          int32_t X, int32_t Y, int32_t Z,
+                          int32_t *ranks_bev, int32_t *ranks_depth, int32_t *ranks_feat,
+                          int32_t *interval_starts, int32_t *interval_lengths,
+                          int32_t *counts_dev,
+                          void *fwd_plan, size_t fwd_plan_bytes,
+                          void *scratch, size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------------------------------
  * Source-compatible L0 symbols.  Same C signatures, semantics (assign into a caller-zeroed
  * (B,Z,Y,X,C) `out`; backward arrays already re-sorted by ranks_feat) and stream behaviour (legacy
  * default stream) as the two launchers bev_pool.cpp declares at :7-14, so the reference's own
