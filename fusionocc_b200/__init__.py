@@ -7,10 +7,11 @@ surface (bykinok/FusionOcc), backed by hand-written CUDA behind a C ABI
 Importing the package does not load the native library; the first op call does, and raises if
 ``fusionocc_b200/lib/libfusionocc_b200.so`` is missing and cannot be built.
 """
-from .bev_pool import (QuickCumsumCuda, TRTBEVPoolv2, VoxelPoolPlan, bev_pool_v2, bev_pool_v2_with_plan,
-                       build_plan, clear_plan_cache)
-from .view_transformer import LSSViewTransformer, rank_prepare
+from .bev_pool import (QuickCumsumCuda, TRTBEVPoolv2, VoxelPoolPlan, bev_pool_v2, bev_pool_v2_cat,
+                       bev_pool_v2_with_plan, build_plan, clear_plan_cache)
+from .view_transformer import LSSViewTransformer, pack_calibration, rank_prepare, rank_prepare_calib
 
 __version__ = '0.1.0'
-__all__ = ['bev_pool_v2', 'bev_pool_v2_with_plan', 'TRTBEVPoolv2', 'QuickCumsumCuda', 'VoxelPoolPlan',
-           'build_plan', 'clear_plan_cache', 'LSSViewTransformer', 'rank_prepare']
+__all__ = ['bev_pool_v2', 'bev_pool_v2_cat', 'bev_pool_v2_with_plan', 'TRTBEVPoolv2', 'QuickCumsumCuda',
+           'VoxelPoolPlan', 'build_plan', 'clear_plan_cache', 'LSSViewTransformer', 'rank_prepare',
+           'rank_prepare_calib', 'pack_calibration']

@@ -35,6 +35,13 @@ SIGNATURES = {
     'fo_bev_pool_v2_forward': (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_void_p, c_int32,
                                        c_int32, c_void_p, c_size_t]),
+    'fo_bev_pool_v2_forward_slice': (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64,
+                                             c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t]),
+    'fo_bev_pool_v2_backward_slice': (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                              c_void_p, c_int64, c_int64, c_int32, c_int64, c_int64, c_int64,
+                                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
+                                              c_size_t]),
     'fo_bwd_plan_bytes': (c_size_t, [c_int64, c_int64]),
     'fo_bwd_plan_build': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                   c_void_p, c_size_t, c_int32, c_int64, c_void_p, c_size_t]),

@@ -29,7 +29,7 @@ import torch
 from . import _cabi
 from ._cabi import FO_LAYOUT_BCZYX, FO_LAYOUT_BZYXC
 
-__all__ = ['bev_pool_v2', 'TRTBEVPoolv2', 'QuickCumsumCuda', 'VoxelPoolPlan', 'build_plan',
+__all__ = ['bev_pool_v2', 'bev_pool_v2_cat', 'TRTBEVPoolv2', 'QuickCumsumCuda', 'VoxelPoolPlan', 'build_plan',
            'clear_plan_cache']
 
 
@@ -152,24 +152,37 @@ def _cached_plan(rb, st, ln, rf, B, n_vox) -> VoxelPoolPlan:
 # ---------------------------------------------------------------------------------------------
 def native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
                    bev_feat_shape: Sequence[int], plan: VoxelPoolPlan,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Launch the forward; returns the fp32 contiguous (B,C,Z,Y,X) tensor."""
+                   out: Optional[torch.Tensor] = None, c_total: Optional[int] = None,
+                   c_offset: int = 0) -> torch.Tensor:
+    """Launch the forward; returns the fp32 contiguous (B,C,Z,Y,X) tensor.  With ``c_total`` the result is
+    written into channels ``[c_offset, c_offset + C)`` of ``out``, a contiguous (B,c_total,Z,Y,X) tensor."""
     lib = _cabi.load()
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
     dev = depth.device
     if out is None:
-        out = torch.empty((B, C, Z, Y, X), dtype=torch.float32, device=dev)
+        out = torch.empty((B, C if c_total is None else c_total, Z, Y, X), dtype=torch.float32, device=dev)
+    flags = _cabi.FO_FWD_ASSUME_SORTED if plan.trusted else 0
     with torch.cuda.device(dev):
-        _cabi.check(lib.fo_bev_pool_v2_forward(
-            _stream(dev), C, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat), _p(ranks_bev),
-            _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals, plan.n_intervals_dev_ptr(),
-            B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, _cabi.FO_FWD_ASSUME_SORTED if plan.trusted else 0,
-            _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward')
+        if c_total is None:
+            _cabi.check(lib.fo_bev_pool_v2_forward(
+                _stream(dev), C, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat), _p(ranks_bev),
+                _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals,
+                plan.n_intervals_dev_ptr(), B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, flags,
+                _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward')
+        else:
+            _cabi.check(lib.fo_bev_pool_v2_forward_slice(
+                _stream(dev), C, _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat), _p(ranks_bev),
+                _p(interval_starts), _p(interval_lengths), plan.n_points, plan.n_intervals,
+                plan.n_intervals_dev_ptr(), B, Z * Y * X, _p(out), FO_LAYOUT_BCZYX, int(c_total), int(c_offset),
+                flags, _p(plan.fwd), plan.fwd.numel()), 'fo_bev_pool_v2_forward_slice')
     return out
 
 
 def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, bev_feat_shape,
-                    plan: VoxelPoolPlan) -> Tuple[torch.Tensor, torch.Tensor]:
+                    plan: VoxelPoolPlan, c_total: Optional[int] = None,
+                    c_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """With ``c_total``, ``out_grad`` is the gradient of the WIDE tensor and only channels
+    ``[c_offset, c_offset + C)`` of it are read."""
     lib = _cabi.load()
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
     dev = depth.device
@@ -180,10 +193,18 @@ def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, b
     sbytes = lib.fo_bwd_scratch_bytes(plan.n_intervals, C, og_layout)
     scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _cabi.check(lib.fo_bev_pool_v2_backward(
-            _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), plan.n_points, plan.n_intervals,
-            B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad), _p(feat_grad),
-            _p(plan.fwd), plan.fwd.numel(), _p(bwd), bwd.numel(), _p(scratch), sbytes), 'fo_bev_pool_v2_backward')
+        if c_total is None:
+            _cabi.check(lib.fo_bev_pool_v2_backward(
+                _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), plan.n_points, plan.n_intervals,
+                B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad), _p(feat_grad),
+                _p(plan.fwd), plan.fwd.numel(), _p(bwd), bwd.numel(), _p(scratch), sbytes),
+                'fo_bev_pool_v2_backward')
+        else:
+            _cabi.check(lib.fo_bev_pool_v2_backward_slice(
+                _stream(dev), C, _p(out_grad), og_layout, int(c_total), int(c_offset), _p(depth), _p(feat),
+                plan.n_points, plan.n_intervals, B, Z * Y * X, depth.numel(), n_feat_rows, _p(depth_grad),
+                _p(feat_grad), _p(plan.fwd), plan.fwd.numel(), _p(bwd), bwd.numel(), _p(scratch), sbytes),
+                'fo_bev_pool_v2_backward_slice')
     return depth_grad, feat_grad
 
 
@@ -257,6 +278,78 @@ def bev_pool_v2_with_plan(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_f
     x = QuickCumsumCuda.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
                               interval_lengths, plan)
     return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+class _PoolCat(torch.autograd.Function):
+    """bev_pool_v2 of several frames written straight into one (B, sum C, Z, Y, X) tensor."""
+
+    @staticmethod
+    def forward(ctx, bev_feat_shape, plans, *flat):
+        n = len(flat) // 7
+        B, Z, Y, X, _ = (int(s) for s in bev_feat_shape)
+        frames = []
+        for i in range(n):
+            depth, feat, rd, rf, rb, st, ln = flat[7 * i:7 * i + 7]
+            _require_cuda(depth, feat, rd, rf, rb, st, ln)
+            frames.append((depth.contiguous().float(), feat.contiguous().float(), rd.contiguous().int(),
+                           rf.contiguous().int(), rb.int().contiguous(), st.contiguous().int(),
+                           ln.contiguous().int()))
+        chans = [f[1].shape[-1] for f in frames]
+        c_total = sum(chans)
+        out = torch.empty((B, c_total, Z, Y, X), dtype=torch.float32, device=frames[0][0].device)
+        used, off = [], 0
+        for i, (depth, feat, rd, rf, rb, st, ln) in enumerate(frames):
+            plan = plans[i] if plans is not None and plans[i] is not None else \
+                _cached_plan(rb, st, ln, rf, B, Z * Y * X)
+            native_forward(depth, feat, rd, rf, rb, st, ln, (B, Z, Y, X, chans[i]), plan, out=out,
+                           c_total=c_total, c_offset=off)
+            used.append(plan)
+            off += chans[i]
+        ctx.save_for_backward(*[t for f in frames for t in f])
+        ctx.plans, ctx.chans, ctx.dims = used, chans, (B, Z, Y, X)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        B, Z, Y, X = ctx.dims
+        c_total = sum(ctx.chans)
+        if out_grad.dtype != torch.float32:
+            out_grad = out_grad.float()
+        if out_grad.is_contiguous():
+            layout = FO_LAYOUT_BCZYX
+        elif out_grad.permute(0, 2, 3, 4, 1).is_contiguous():
+            layout = FO_LAYOUT_BZYXC                              # channels-last-3d upstream
+        else:
+            out_grad, layout = out_grad.contiguous(), FO_LAYOUT_BCZYX
+        saved = ctx.saved_tensors
+        grads, off = [], 0
+        for i, c in enumerate(ctx.chans):
+            depth, feat, rd, rf, rb, st, ln = saved[7 * i:7 * i + 7]
+            if ctx.needs_input_grad[2 + 7 * i] or ctx.needs_input_grad[3 + 7 * i]:
+                dg, fg = native_backward(out_grad, layout, depth, feat, rd, rf, (B, Z, Y, X, c), ctx.plans[i],
+                                         c_total=c_total, c_offset=off)
+            else:
+                dg = fg = None
+            grads += [dg, fg, None, None, None, None, None]
+            off += c
+        return (None, None, *grads)
+
+
+def bev_pool_v2_cat(frames, bev_feat_shape, plans=None):
+    """``torch.cat([bev_pool_v2(*f, bev_feat_shape, ...) for f in frames], dim=1)`` without the concatenation
+    (the consumer pattern of fusion_occ.py:316-326): every frame's splat is written directly
+    into its channel slice of ONE (B, sum C, Z, Y, X) tensor, and the backward reads each frame's slice of the
+    incoming gradient in place.
+
+    ``frames``: sequence of ``(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+    interval_lengths)`` with the argument meaning of :func:`bev_pool_v2`; ``bev_feat_shape = (B,Z,Y,X,C)``
+    (C is taken per frame from ``feat``).  Results are bit-identical to the concatenation.
+    """
+    flat = [t for f in frames for t in f]
+    if len(flat) != 7 * len(frames) or not frames:
+        raise ValueError('every frame is a 7-tuple (depth, feat, ranks_depth, ranks_feat, ranks_bev, '
+                         'interval_starts, interval_lengths)')
+    return _PoolCat.apply(tuple(int(s) for s in bev_feat_shape), plans, *flat)
 
 
 class TRTBEVPoolv2(torch.autograd.Function):

@@ -18,7 +18,8 @@
 namespace fo {
 
 struct GatherArgs {
-    const float *og;                // (B,C,Z,Y,X)
+    const float *og;                // (B,C,Z,Y,X), possibly a channel slice of a wider tensor
+    int64_t og_bstride;             // elements between samples
     int32_t C;
     int64_t V;
     const FwdPlanHeader *hdr;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
         if ((unsigned)my_v >= (unsigned)nv) my_v = -1;
     }
     const unsigned occ = __reduce_or_sync(0xffffffffu, my_v >= 0 ? (1u << my_v) : 0u);
-    const float *plane0 = a.og + ((int64_t)b * C) * a.V + v0;
+    const float *plane0 = a.og + (int64_t)b * a.og_bstride + v0;
     if ((a.V & 3) == 0) {
         const int riq = lane >> 3, chunk = lane & 7;
         if (((occ >> (4 * chunk)) & 0xFu) != 0u) {
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
 
 struct PixelArgs {
     const float *G;                 // gathered rows [n_intervals, C]  or  out_grad in (B,Z,Y,X,C)
+    int32_t g_rowstride;            // elements between rows of G (C; C_total for a channel slice of (B,Z,Y,X,C_total))
     const int32_t *row_map;         // nullptr: G row = entry's interval id; else G row = row_map[interval id]
     const float *depth, *feat;
     const int32_t *ent_p, *ent_iv;  // backward plan entries
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
                 for (int t = 0; t < U; ++t) r[t] = rec[j + t];
 #pragma unroll
                 for (int t = 0; t < U; ++t) {
-                    const int base = max(r[t].x, 0) * C + lane;      // invalid rows read row 0 and are discarded
+                    const int base = max(r[t].x, 0) * a.g_rowstride + lane;      // invalid rows read row 0 and are discarded
 #pragma unroll
                     for (int k = 0; k < NACC; ++k) g[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.G + base + 32 * k) : 0.f;
                 }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_scalar_kernel(PixelArgs
             for (int j = 0; j < len; ++j) {
                 const int p = a.ent_p[s + j], row = row_of(j);
                 if (p < 0 || p >= a.n_depth || row < 0) continue;
-                sum = fmaf(a.G[(int64_t)row * C + c], a.depth[p], sum);
+                sum = fmaf(a.G[(int64_t)row * a.g_rowstride + c], a.depth[p], sum);
             }
             a.feat_grad[(int64_t)q * C + c] = sum;
         }
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_scalar_kernel(PixelArgs
             const int p = a.ent_p[s + j], row = row_of(j);
             if (p < 0 || p >= a.n_depth || row < 0) continue;
             float sum = 0.f;
-            for (int c = 0; c < C; ++c) sum = fmaf(a.G[(int64_t)row * C + c], a.feat[(int64_t)q * C + c], sum);
+            for (int c = 0; c < C; ++c) sum = fmaf(a.G[(int64_t)row * a.g_rowstride + c], a.feat[(int64_t)q * C + c], sum);
             a.depth_grad[p] = sum;
         }
     }
@@ -344,7 +346,7 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
     const int C = pa.C;
     const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C) * sizeof(float);
     const int nacc = (C + 31) / 32;
-    const bool idx32 = pa.n_rows_G * C < INT_MAX && pa.n_feat_rows * C < INT_MAX && pixels < INT_MAX;
+    const bool idx32 = pa.n_rows_G * pa.g_rowstride < INT_MAX && pa.n_feat_rows * C < INT_MAX && pixels < INT_MAX;
     if (vec && idx32 && nacc <= 4 && smem <= 200 * 1024) {
         const int blocks = grid_for(pixels, kPixWarps, 8);
 #define FO_PIX(NA, EX)                                                                                          \
@@ -378,13 +380,14 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
 }
 }  // namespace
 
-extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const float *out_grad, int32_t og_layout,
-                                       const float *depth, const float *feat, int64_t n_points,
-                                       int64_t n_intervals, int32_t B, int64_t n_vox, int64_t n_depth,
-                                       int64_t n_feat_rows, float *depth_grad, float *feat_grad,
-                                       const void *fwd_plan, size_t fwd_plan_bytes, const void *bwd_plan,
-                                       size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t og_layout, int32_t c_total,
+                  int32_t c_offset, const float *depth, const float *feat, int64_t n_points, int64_t n_intervals,
+                  int32_t B, int64_t n_vox, int64_t n_depth, int64_t n_feat_rows, float *depth_grad,
+                  float *feat_grad, const void *fwd_plan, size_t fwd_plan_bytes, const void *bwd_plan,
+                  size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    FO_CHECK_ARG(c >= 1 && c_offset >= 0 && c_total >= c && c_offset + c <= c_total,
+                 "channel slice [%d, %d) does not fit %d channels", c_offset, c_offset + c, c_total);
     FO_CHECK_ARG(c >= 1 && B >= 1 && n_vox >= 1, "c, B and voxels per sample must be positive");
     FO_CHECK_ARG(og_layout == FO_LAYOUT_BCZYX || og_layout == FO_LAYOUT_BZYXC, "unknown og_layout %d", og_layout);
     FO_CHECK_ARG(depth_grad && feat_grad, "NULL gradient output");
@@ -418,7 +421,7 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
         const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
         if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
         GatherArgs ga;
-        ga.og = out_grad; ga.C = c; ga.V = n_vox;
+        ga.og = out_grad + (int64_t)c_offset * n_vox; ga.og_bstride = (int64_t)c_total * n_vox; ga.C = c; ga.V = n_vox;
         ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
         const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
         if (n_ctas > 65535 || B > 65535 || c > 256)
@@ -452,12 +455,36 @@ extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const flo
         }
 #undef FO_GATHER
         FO_LAUNCH_CHECK("bwd_gather_kernel");
-        pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals;
+        pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals; pa.g_rowstride = c;
     } else {
-        pa.G = out_grad; pa.row_map = pv.iv_vox; pa.n_rows_G = (int64_t)B * n_vox;
+        pa.G = out_grad + c_offset; pa.row_map = pv.iv_vox; pa.n_rows_G = (int64_t)B * n_vox; pa.g_rowstride = c_total;
     }
-    const bool pvec = vec && (((uintptr_t)pa.G & 15) == 0);
+    const bool pvec = vec && (((uintptr_t)pa.G & 15) == 0) && (pa.g_rowstride % 4 == 0);
     return launch_pixel(pa, pvec, stream);
+}
+}  // namespace
+
+extern "C" int fo_bev_pool_v2_backward(fo_stream_t stream_, int32_t c, const float *out_grad, int32_t og_layout,
+                                       const float *depth, const float *feat, int64_t n_points,
+                                       int64_t n_intervals, int32_t B, int64_t n_vox, int64_t n_depth,
+                                       int64_t n_feat_rows, float *depth_grad, float *feat_grad,
+                                       const void *fwd_plan, size_t fwd_plan_bytes, const void *bwd_plan,
+                                       size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    return backward_impl((cudaStream_t)stream_, c, out_grad, og_layout, c, 0, depth, feat, n_points, n_intervals, B,
+                         n_vox, n_depth, n_feat_rows, depth_grad, feat_grad, fwd_plan, fwd_plan_bytes, bwd_plan,
+                         bwd_plan_bytes, scratch, scratch_bytes);
+}
+
+extern "C" int fo_bev_pool_v2_backward_slice(fo_stream_t stream_, int32_t c, const float *out_grad,
+                                             int32_t og_layout, int32_t c_total, int32_t c_offset,
+                                             const float *depth, const float *feat, int64_t n_points,
+                                             int64_t n_intervals, int32_t B, int64_t n_vox, int64_t n_depth,
+                                             int64_t n_feat_rows, float *depth_grad, float *feat_grad,
+                                             const void *fwd_plan, size_t fwd_plan_bytes, const void *bwd_plan,
+                                             size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    return backward_impl((cudaStream_t)stream_, c, out_grad, og_layout, c_total, c_offset, depth, feat, n_points,
+                         n_intervals, B, n_vox, n_depth, n_feat_rows, depth_grad, feat_grad, fwd_plan, fwd_plan_bytes,
+                         bwd_plan, bwd_plan_bytes, scratch, scratch_bytes);
 }
 
 // Source-compatible launcher: bev_pool.cpp:11-14 / bev_pool_cuda.cu:133-140 semantics — arrays are

@@ -32,6 +32,8 @@ struct FwdArgs {
     float *out;
     const FwdPlanHeader *hdr;
     const int32_t *sub_pt;
+    int64_t out_bstride;            // (B,C,Z,Y,X) output: elements between samples (C_total * V; C * V when not a slice)
+    int64_t out_rowstride;          // (B,Z,Y,X,C) output: elements between voxels   (C_total; C when not a slice)
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
 };
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
     const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
     const unsigned lane_rot = ((unsigned)lane & 7u) << 4;             // its rotation, in bytes
-    float *pl = a.out + ((int64_t)b * C + riq) * V + v0;             // row riq of this sub-tile's block
+    float *pl = a.out + (int64_t)b * a.out_bstride + (int64_t)riq * V + v0;             // row riq of this sub-tile's block
     const bool staged = pa < pb || (in_range && !vec_out);
 
     if (W == 1 && !staged) {                              // empty sub-tile: stream zeros, no staging
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
             const int nv_w = st ? min(kSub, (int)V - (su_w << kSubShift)) : 0;
             const bool wr = 4 * chunk < nv_w;
             const unsigned sw = (unsigned)__cvta_generic_to_shared(smem + w * C * kSub);
-            float *dst = a.out + (int64_t)b * C * V + ((int64_t)su_w << kSubShift) + 4 * chunk;
+            float *dst = a.out + (int64_t)b * a.out_bstride + ((int64_t)su_w << kSubShift) + 4 * chunk;
             for (int c = warp; c < C; c += W) {
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (st == 2) x = lds_f4(sw + ((unsigned)c << 7) + ((unsigned)((chunk + c) & 7) << 4));
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
                 }
             }
         } else {
-            float *plane0 = a.out + ((int64_t)b * C) * V + v0;
+            float *plane0 = a.out + (int64_t)b * a.out_bstride + v0;
             for (int e = lane; e < C * kSub; e += 32) {
                 const int c = e >> kSubShift, v = e & (kSub - 1);
                 if (v < nv) __stcs(plane0 + (int64_t)c * V + v, stage[stage_index(c, v)]);
@@ -283,10 +285,10 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
         }
     } else {
         // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
-        float *dst = a.out + ((int64_t)bV + v0) * C;
+        float *dst = a.out + ((int64_t)bV + v0) * a.out_rowstride;
         for (int e = lane; e < nv * C; e += 32) {
             const int v = e / C, c = e - v * C;
-            __stcs(dst + e, stage[stage_index(c, v)]);
+            __stcs(dst + (int64_t)v * a.out_rowstride + c, stage[stage_index(c, v)]);
         }
     }
 }
@@ -298,13 +300,27 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
 // arbitrary interval order) and (c) for channel counts too large for the staged tile.  Invalid
 // intervals are skipped instead of writing out of bounds.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) zero_if_flag_kernel(float4 *out, int64_t n4, float *tail, int n_tail,
-                                                           const FwdPlanHeader *hdr, int need_flag) {
+// zero-fills n_runs runs of run_len floats, run_stride floats apart (one run per sample of a (B,C,Z,Y,X) channel
+// slice; one run per voxel of a (B,Z,Y,X,C) slice; a single run when the output is not a slice)
+__global__ void __launch_bounds__(256) zero_if_flag_kernel(float *out, int64_t n_runs, int64_t run_len,
+                                                           int64_t run_stride, int vec, const FwdPlanHeader *hdr,
+                                                           int need_flag) {
     if (need_flag && !(hdr->flags & kFlagUnsorted)) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
-        __stcs(out + i, make_float4(0.f, 0.f, 0.f, 0.f));
-    if (blockIdx.x == 0 && threadIdx.x < n_tail) tail[threadIdx.x] = 0.f;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t per = run_len >> 2, total = n_runs * per;
+        for (int64_t i = gtid; i < total; i += stride) {
+            const int64_t r = i / per, e = i - r * per;
+            __stcs(reinterpret_cast<float4 *>(out + r * run_stride) + e, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    } else {
+        const int64_t total = n_runs * run_len;
+        for (int64_t i = gtid; i < total; i += stride) {
+            const int64_t r = i / run_len, e = i - r * run_len;
+            out[r * run_stride + e] = 0.f;
+        }
+    }
 }
 
 template <int LAYOUT>
@@ -326,8 +342,8 @@ __global__ void __launch_bounds__(256) fwd_scatter_kernel(FwdArgs a, int need_fl
             float psum = 0.f;
             for (int i = 0; i < len; ++i)
                 psum = fmaf(a.feat[(int64_t)a.rf[s + i] * C + c], a.depth[a.rd[s + i]], psum);
-            if (LAYOUT == FO_LAYOUT_BCZYX) a.out[(b * C + c) * a.V + vin] = psum;
-            else a.out[(int64_t)v * C + c] = psum;
+            if (LAYOUT == FO_LAYOUT_BCZYX) a.out[b * a.out_bstride + c * a.V + vin] = psum;
+            else a.out[(int64_t)v * a.out_rowstride + c] = psum;
         }
     }
 }
@@ -370,14 +386,15 @@ int launch_dense_any(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t str
 }
 }  // namespace
 
-extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const float *depth, const float *feat,
-                                      const int32_t *ranks_depth, const int32_t *ranks_feat,
-                                      const int32_t *ranks_bev, const int32_t *interval_starts,
-                                      const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
-                                      const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, float *out,
-                                      int32_t out_layout, int32_t flags, const void *plan, size_t plan_bytes) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float *feat, const int32_t *ranks_depth,
+                 const int32_t *ranks_feat, const int32_t *ranks_bev, const int32_t *interval_starts,
+                 const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
+                 const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, float *out, int32_t out_layout,
+                 int32_t c_total, int32_t c_offset, int32_t flags, const void *plan, size_t plan_bytes) {
     FO_CHECK_ARG(c >= 1, "channels must be positive (got %d)", c);
+    FO_CHECK_ARG(c_offset >= 0 && c_total >= c && c_offset + c <= c_total,
+                 "channel slice [%d, %d) does not fit %d channels", c_offset, c_offset + c, c_total);
     FO_CHECK_ARG(B >= 1 && n_vox >= 1, "B and voxels per sample must be positive");
     FO_CHECK_ARG(out != nullptr && ((uintptr_t)out & 15) == 0, "out must be non-NULL and 16-byte aligned");
     FO_CHECK_ARG(out_layout == FO_LAYOUT_BCZYX || out_layout == FO_LAYOUT_BZYXC, "unknown out_layout %d", out_layout);
@@ -391,7 +408,11 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     a.depth = depth; a.feat = feat; a.rd = ranks_depth; a.rf = ranks_feat; a.rb = ranks_bev;
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = n_points; a.n_intervals = n_intervals; a.n_intervals_dev = n_intervals_dev;
-    a.C = c; a.B = B; a.V = n_vox; a.out = out; a.hdr = pv.hdr; a.sub_pt = pv.sub_pt;
+    a.C = c; a.B = B; a.V = n_vox; a.hdr = pv.hdr; a.sub_pt = pv.sub_pt;
+    // a channel slice [c_offset, c_offset + c) of a wider tensor: only the sample / voxel strides change
+    a.out = out + (out_layout == FO_LAYOUT_BCZYX ? (int64_t)c_offset * n_vox : (int64_t)c_offset);
+    a.out_bstride = (int64_t)c_total * n_vox;
+    a.out_rowstride = c_total;
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
     const size_t smem = (size_t)kFwdWarps * kSub * c * sizeof(float);
@@ -407,10 +428,12 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
     // the staged tile does not fit shared memory.
     const int need_flag = dense_ok ? 1 : 0;
     if (dense_ok && (flags & FO_FWD_ASSUME_SORTED)) return FO_OK;
-    const int64_t total = (int64_t)B * n_vox * c;
-    const int64_t n4 = total / 4;
-    const int n_tail = (int)(total - n4 * 4);
-    zero_if_flag_kernel<<<148 * 8, 256, 0, stream>>>((float4 *)out, n4, out + n4 * 4, n_tail, pv.hdr, need_flag);
+    int64_t n_runs, run_len, run_stride;
+    if (c_total == c) { n_runs = 1; run_len = (int64_t)B * n_vox * c; run_stride = 0; }
+    else if (out_layout == FO_LAYOUT_BCZYX) { n_runs = B; run_len = (int64_t)c * n_vox; run_stride = a.out_bstride; }
+    else { n_runs = (int64_t)B * n_vox; run_len = c; run_stride = c_total; }
+    const int vec = (run_len % 4 == 0) && (run_stride % 4 == 0) && (((uintptr_t)a.out & 15) == 0);
+    zero_if_flag_kernel<<<148 * 8, 256, 0, stream>>>(a.out, n_runs, run_len, run_stride, vec, pv.hdr, need_flag);
     FO_LAUNCH_CHECK("zero_if_flag_kernel");
     const int blocks = grid_for(n_intervals * 32, 256, 8);
     if (out_layout == FO_LAYOUT_BCZYX)
@@ -419,6 +442,30 @@ extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const floa
         fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<blocks, 256, 0, stream>>>(a, need_flag);
     FO_LAUNCH_CHECK("fwd_scatter_kernel");
     return FO_OK;
+}
+}  // namespace
+
+extern "C" int fo_bev_pool_v2_forward(fo_stream_t stream_, int32_t c, const float *depth, const float *feat,
+                                      const int32_t *ranks_depth, const int32_t *ranks_feat,
+                                      const int32_t *ranks_bev, const int32_t *interval_starts,
+                                      const int32_t *interval_lengths, int64_t n_points, int64_t n_intervals,
+                                      const int32_t *n_intervals_dev, int32_t B, int64_t n_vox, float *out,
+                                      int32_t out_layout, int32_t flags, const void *plan, size_t plan_bytes) {
+    return forward_impl((cudaStream_t)stream_, c, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                        interval_lengths, n_points, n_intervals, n_intervals_dev, B, n_vox, out, out_layout, c, 0,
+                        flags, plan, plan_bytes);
+}
+
+extern "C" int fo_bev_pool_v2_forward_slice(fo_stream_t stream_, int32_t c, const float *depth, const float *feat,
+                                            const int32_t *ranks_depth, const int32_t *ranks_feat,
+                                            const int32_t *ranks_bev, const int32_t *interval_starts,
+                                            const int32_t *interval_lengths, int64_t n_points,
+                                            int64_t n_intervals, const int32_t *n_intervals_dev, int32_t B,
+                                            int64_t n_vox, float *out, int32_t out_layout, int32_t c_total,
+                                            int32_t c_offset, int32_t flags, const void *plan, size_t plan_bytes) {
+    return forward_impl((cudaStream_t)stream_, c, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                        interval_lengths, n_points, n_intervals, n_intervals_dev, B, n_vox, out, out_layout, c_total,
+                        c_offset, flags, plan, plan_bytes);
 }
 
 // Source-compatible launcher: semantics of bev_pool.cpp:7-9 / bev_pool_cuda.cu:125-131 — assign into a
@@ -432,6 +479,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.starts = interval_starts; a.lengths = interval_lengths;
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
-    a.sps = 0; a.check_flags = 0;
+    a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

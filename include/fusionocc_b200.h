@@ -110,6 +110,21 @@ int fo_bev_pool_v2_forward(fo_stream_t stream, int32_t c,
                            float *out, int32_t out_layout, int32_t flags,
                            const void *plan, size_t plan_bytes);
 
+/* Same, writing a CHANNEL SLICE [c_offset, c_offset + c) of a wider voxel tensor with c_total channels
+ * ((B,c_total,Z,Y,X) or (B,Z,Y,X,c_total), `out` = base of the wide tensor): what the consumer builds
+ * with torch.cat over temporal frames (projects/FusionOcc/fusionocc/detectors/fusion_occ.py:316-326) is
+ * written in place, one call per frame, no concatenation copy.  Only the slice is
+ * written. */
+int fo_bev_pool_v2_forward_slice(fo_stream_t stream, int32_t c,
+                                 const float *depth, const float *feat,
+                                 const int32_t *ranks_depth, const int32_t *ranks_feat,
+                                 const int32_t *ranks_bev,
+                                 const int32_t *interval_starts, const int32_t *interval_lengths,
+                                 int64_t n_points, int64_t n_intervals, const int32_t *n_intervals_dev,
+                                 int32_t B, int64_t n_voxels_per_sample,
+                                 float *out, int32_t out_layout, int32_t c_total, int32_t c_offset,
+                                 int32_t flags, const void *plan, size_t plan_bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward plan = the inverse interval ordering: forward positions regrouped by ranks_feat (stable),
  * i.e. the arrays the reference rebuilds with argsort / where on every backward
@@ -156,6 +171,19 @@ int fo_bev_pool_v2_backward(fo_stream_t stream, int32_t c,
                             const void *fwd_plan, size_t fwd_plan_bytes,
                             const void *bwd_plan, size_t bwd_plan_bytes,
                             void *scratch, size_t scratch_bytes);
+
+/* Same, reading the gradient of a channel slice [c_offset, c_offset + c) out of the gradient of the wide
+ * tensor (`out_grad` = base of the (B,c_total,Z,Y,X) / (B,Z,Y,X,c_total) gradient): no slicing copy. */
+int fo_bev_pool_v2_backward_slice(fo_stream_t stream, int32_t c,
+                                  const float *out_grad, int32_t og_layout, int32_t c_total, int32_t c_offset,
+                                  const float *depth, const float *feat,
+                                  int64_t n_points, int64_t n_intervals,
+                                  int32_t B, int64_t n_voxels_per_sample,
+                                  int64_t n_depth, int64_t n_feat_rows,
+                                  float *depth_grad, float *feat_grad,
+                                  const void *fwd_plan, size_t fwd_plan_bytes,
+                                  const void *bwd_plan, size_t bwd_plan_bytes,
+                                  void *scratch, size_t scratch_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Rank precompute.  Replaces view_transformer.py:223-281 (about 50 eager torch launches, >= 4 host
