@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
             if (j < len) {
                 if (len > 1) a.sorted[s + j] = v[j];
                 if (kForward) {
-                    a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
+                    if (a.ranks_feat) a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
                     a.ranks_bev[s + j] = bucket;
                 }
             }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
         if (kForward) {
             for (int j = lane; j < ll; j += 32) {
                 const int p = a.sorted[ls + j];
-                a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                if (a.ranks_feat) a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
                 a.ranks_bev[ls + j] = lb;
             }
         }
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
         if (kForward) {
             for (int j = threadIdx.x; j < ll; j += kSortThreads) {
                 const int p = a.sorted[ls + j];
-                a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                if (a.ranks_feat) a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
                 a.ranks_bev[ls + j] = lb;
             }
         }

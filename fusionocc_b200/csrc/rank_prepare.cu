@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) count_keys_kernel(const int32_t *__restri
     const int64_t n = n_dev ? min((int64_t)max(*n_dev, 0), n_cap) : n_cap;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid == 0) { hdr->n_bwd_intervals = 0; hdr->n_points = (int)n; }
+    if (gtid == 0 && hdr) { hdr->n_bwd_intervals = 0; hdr->n_points = (int)n; }
     for (int64_t i = gtid; i < n; i += stride) {
         const int k = keys[i];
         slot[i] = (k >= 0 && k < n_buckets) ? atomicAdd(cnt + k, 1) : -1;
@@ -559,6 +559,67 @@ extern "C" int fo_rank_prepare_calib(fo_stream_t stream_, const float *frustum, 
     return rank_prepare_impl((cudaStream_t)stream_, nullptr, &g, B, N, D, H, W, lower_bound, interval, X, Y, Z,
                              ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths, counts_dev,
                              fwd_plan, fwd_plan_bytes, scratch, scratch_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rank pipeline from caller-supplied integer bucket ids (sibling ops bev_pool v1 / occ_pool, SURVEY.md §8f-4:
+// projects/BEVFusion/bevfusion/ops/bev_pool/bev_pool.py:85-99 computes ranks from integer coords, argsorts and
+// re-discovers the runs with torch ops).  Same stable one-digit bucket sort as fo_rank_prepare.
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t fo_rank_from_keys_scratch_bytes(int64_t n_points, int64_t n_buckets) {
+    if (n_points < 0 || n_buckets < 1) return 0;
+    const int64_t cap_iv = n_points < n_buckets ? n_points : n_buckets;
+    return bucket_zero_bytes(n_buckets) + (size_t)align_up(n_points * 4, 256) + (size_t)align_up(cap_iv * 4, 256);
+}
+
+extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64_t n_points, int64_t n_buckets,
+                                 int32_t *sorted_keys, int32_t *order, int32_t *interval_starts,
+                                 int32_t *interval_lengths, int32_t *counts_dev, void *scratch,
+                                 size_t scratch_bytes) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FO_CHECK_ARG(n_points >= 0 && n_points < INT_MAX && n_buckets >= 1 && n_buckets < INT_MAX, "bad sizes");
+    FO_CHECK_ARG(counts_dev != nullptr, "counts_dev is NULL");
+    FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
+    if (n_points == 0) return FO_OK;
+    FO_CHECK_ARG(keys && sorted_keys && order && interval_starts && interval_lengths, "NULL array");
+    FO_CHECK_ARG(scratch != nullptr && ((uintptr_t)scratch & 255) == 0, "scratch must be non-NULL, 256-byte aligned");
+    const size_t need = fo_rank_from_keys_scratch_bytes(n_points, n_buckets);
+    if (scratch_bytes < need)
+        return set_error(FO_ERR_SCRATCH, "rank scratch is %zu bytes, need %zu", scratch_bytes, need);
+    SortScratch ss = sort_scratch_view(scratch, n_buckets);
+    int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
+    int32_t *iv_bucket = (int32_t *)((char *)slot + align_up(n_points * 4, 256));
+    FO_CUDA(cudaMemsetAsync(scratch, 0, ss.zero_bytes, stream));
+    count_keys_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(keys, n_points, nullptr, n_buckets, ss.cnt, slot,
+                                                                   nullptr);
+    FO_LAUNCH_CHECK("count_keys_kernel");
+    ScanArgs sa;
+    sa.cnt = ss.cnt; sa.n_buckets = n_buckets;
+    sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = iv_bucket;
+    sa.bucket2iv = nullptr;
+    sa.totals = counts_dev;
+    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
+    sa.fwd_hdr = nullptr; sa.bwd_hdr = nullptr;
+    sa.agg = ss.agg;
+    const int scan_blocks = (int)((n_buckets + kScanTile - 1) / kScanTile);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_buckets, ss.agg);
+    FO_LAUNCH_CHECK("tile_reduce_kernel");
+    scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
+    FO_LAUNCH_CHECK("scan_buckets_kernel");
+    place_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(keys, slot, ss.cnt, n_points, nullptr, n_buckets, order);
+    FO_LAUNCH_CHECK("place_kernel");
+    OrderArgs oa;
+    oa.sorted = order; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
+    oa.iv_bucket = iv_bucket; oa.n_intervals = counts_dev + 1;
+    oa.ranks_feat = nullptr; oa.ranks_bev = sorted_keys;
+    oa.dhw = 1; oa.hw = 1;
+    oa.long_list = slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)n_points;
+    const int64_t cap_iv = n_points < n_buckets ? n_points : n_buckets;
+    order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_short_kernel<keys>");
+    order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
+    FO_LAUNCH_CHECK("order_long_kernel<keys>");
+    return FO_OK;
 }
 
 extern "C" size_t fo_bwd_plan_bytes(int64_t n_points_capacity, int64_t n_feat_rows) {

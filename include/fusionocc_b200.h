@@ -242,6 +242,25 @@ int fo_rank_prepare_calib(fo_stream_t stream, const float *frustum, const float 
                           void *scratch, size_t scratch_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * Rank pipeline from integer bucket ids — the sibling ops with the same sort -> interval -> reduce skeleton
+ * (SURVEY.md §8f-4): bev_pool v1 (projects/BEVFusion/bevfusion/ops/bev_pool/bev_pool.py:85-99: ranks from
+ * integer coords, argsort, kept/where interval rebuild) and occ_pool (projects/CONet/.../occ_pooling/
+ * OCC_Pool.py:39-71).  Stable: ties keep ascending original index.
+ *
+ *   keys              int32 [n_points]  bucket (voxel) id in [0, n_buckets); anything else drops the point
+ *   sorted_keys       int32 [n_points]  out: keys in sorted order                    (= ranks_bev)
+ *   order             int32 [n_points]  out: original index of every sorted position (= ranks_depth/_feat)
+ *   interval_starts / interval_lengths  out, capacity min(n_points, n_buckets)
+ *   counts_dev        int32[4] on device: {n_kept, n_intervals, 0, 0}
+ * ------------------------------------------------------------------------------------------------ */
+size_t fo_rank_from_keys_scratch_bytes(int64_t n_points, int64_t n_buckets);
+
+int fo_rank_from_keys(fo_stream_t stream, const int32_t *keys, int64_t n_points, int64_t n_buckets,
+                      int32_t *sorted_keys, int32_t *order,
+                      int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev,
+                      void *scratch, size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------------------------------
  * Source-compatible L0 symbols.  Same C signatures, semantics (assign into a caller-zeroed
  * (B,Z,Y,X,C) `out`; backward arrays already re-sorted by ranks_feat) and stream behaviour (legacy
  * default stream) as the two launchers bev_pool.cpp declares at :7-14, so the reference's own
