@@ -65,7 +65,7 @@ SIGNATURES = {
     'fo_view_transform_host_workspace_bytes': (c_size_t, [c_int32] * 10),
     'fo_view_transform_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, _f3, _f3, c_int32, c_int32, c_int32, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -91,8 +91,9 @@ extern "C" int fo_view_transform_host(fo_stream_t stream_, const float *coor_hos
                                       int32_t D, int32_t H, int32_t W, int32_t c, const float lower_bound[3],
                                       const float interval[3], int32_t X, int32_t Y, int32_t Z, float *out_host,
                                       float *depth_grad_host, float *feat_grad_host, int32_t counts_host[4],
-                                      void *workspace_dev, size_t workspace_bytes) {
+                                      void *workspace_dev, size_t workspace_bytes, fo_stream_t upload_stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    cudaStream_t up = upload_stream_ ? (cudaStream_t)upload_stream_ : stream;
     FO_CHECK_ARG(B >= 1 && N >= 1 && D >= 1 && H >= 1 && W >= 1 && c >= 1 && X >= 1 && Y >= 1 && Z >= 1,
                  "non-positive dimension");
     FO_CHECK_ARG(coor_host && depth_host && feat_host && out_host && workspace_dev, "NULL buffer");
@@ -108,7 +109,23 @@ extern "C" int fo_view_transform_host(fo_stream_t stream_, const float *coor_hos
     FO_CUDA(cudaMemcpyAsync(w.coor, coor_host, (size_t)P * 12, cudaMemcpyHostToDevice, stream));
     FO_CUDA(cudaMemcpyAsync(w.depth, depth_host, (size_t)P * 4, cudaMemcpyHostToDevice, stream));
     FO_CUDA(cudaMemcpyAsync(w.feat, feat_host, (size_t)rows * c * 4, cudaMemcpyHostToDevice, stream));
-    if (bwd) FO_CUDA(cudaMemcpyAsync(w.og, out_grad_host, (size_t)NV * c * 4, cudaMemcpyHostToDevice, stream));
+    // The 82 MB/sample out_grad upload is not needed before the backward: on a second stream it overlaps the
+    // forward and, PCIe being full duplex, the 82 MB/sample download of the voxel tensor.
+    cudaEvent_t og_ready = nullptr;
+    if (bwd) {
+        if (up != stream) {
+            cudaEvent_t ws_free;
+            FO_CUDA(cudaEventCreateWithFlags(&ws_free, cudaEventDisableTiming));
+            FO_CUDA(cudaEventRecord(ws_free, stream));             // earlier users of the workspace are done
+            FO_CUDA(cudaStreamWaitEvent(up, ws_free, 0));
+            FO_CUDA(cudaEventDestroy(ws_free));
+        }
+        FO_CUDA(cudaMemcpyAsync(w.og, out_grad_host, (size_t)NV * c * 4, cudaMemcpyHostToDevice, up));
+        if (up != stream) {
+            FO_CUDA(cudaEventCreateWithFlags(&og_ready, cudaEventDisableTiming));
+            FO_CUDA(cudaEventRecord(og_ready, up));
+        }
+    }
 
     if (int rc = fo_rank_prepare(stream_, w.coor, B, N, D, H, W, lower_bound, interval, X, Y, Z, w.rb, w.rd, w.rf,
                                  w.st, w.ln, w.counts, w.fwd_plan, w.fwd_plan_bytes, w.rank_scratch,
@@ -120,6 +137,10 @@ extern "C" int fo_view_transform_host(fo_stream_t stream_, const float *coor_hos
         return rc;
     FO_CUDA(cudaMemcpyAsync(out_host, w.out, (size_t)NV * c * 4, cudaMemcpyDeviceToHost, stream));
     if (bwd) {
+        if (og_ready) {
+            FO_CUDA(cudaStreamWaitEvent(stream, og_ready, 0));
+            FO_CUDA(cudaEventDestroy(og_ready));
+        }
         if (int rc = fo_bwd_plan_build(stream_, w.rd, w.rf, P, w.counts, P, rows, H * W, FO_BWD_PLAN_STRUCTURED,
                                        w.fwd_plan, w.fwd_plan_bytes, B, V, w.bwd_plan, w.bwd_plan_bytes))
             return rc;

@@ -279,7 +279,9 @@ void fo_compat_bev_pool_v2_grad(int c, int n_intervals, const float *out_grad,
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (end-to-end measurement and non-torch hosts): H2D of the inputs,
  * rank precompute + forward (+ backward when out_grad_host != NULL), D2H of the results, all on
- * `stream`, using a caller-provided device workspace.  Host buffers should be pinned.
+ * `stream`, using a caller-provided device workspace.  Host buffers should be pinned.  `upload_stream`
+ * (may be NULL = `stream`) carries the out_grad upload, so that it overlaps the forward and the download
+ * of the voxel tensor; the call orders the two streams with events and returns without synchronising.
  * ------------------------------------------------------------------------------------------------ */
 size_t fo_view_transform_host_workspace_bytes(int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
                                               int32_t c, int32_t X, int32_t Y, int32_t Z,
@@ -294,7 +296,8 @@ int fo_view_transform_host(fo_stream_t stream,
                            float *out_host /* (B,c,Z,Y,X) */,
                            float *depth_grad_host, float *feat_grad_host,
                            int32_t counts_host[4],
-                           void *workspace_dev, size_t workspace_bytes);
+                           void *workspace_dev, size_t workspace_bytes,
+                           fo_stream_t upload_stream);
 
 #ifdef __cplusplus
 }

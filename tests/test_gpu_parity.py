@@ -426,8 +426,10 @@ def test_compat_l0_symbols_match_reference_launcher_semantics():
     assert_bit_equal(fg, wfg, 'compat feat_grad')
 
 
-def test_host_buffer_entry_point():
-    """fo_view_transform_host: pinned host buffers in, host buffers out (the e2e leg of bench.py)."""
+@pytest.mark.parametrize('two_streams', [False, True])
+def test_host_buffer_entry_point(two_streams):
+    """fo_view_transform_host: pinned host buffers in, host buffers out (the e2e leg of bench.py); with a
+    second stream the out_grad upload overlaps the forward and the voxel download."""
     import ctypes
     from fusionocc_b200 import _cabi
     from fusionocc_b200.rig import make_out_grad
@@ -450,9 +452,11 @@ def test_host_buffer_entry_point():
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev())
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     s = torch.cuda.current_stream()
+    up = torch.cuda.Stream() if two_streams else None
     rc = lib.fo_view_transform_host(ctypes.c_void_p(s.cuda_stream), p(h_coor), p(h_depth), p(h_feat), p(h_og),
                                     B, N, D, H, W, C, _cabi.f3(case['lb']), _cabi.f3(case['itv']), X, Y, Z,
-                                    p(h_out), p(h_dg), p(h_fg), p(h_counts), p(ws), ws_bytes)
+                                    p(h_out), p(h_dg), p(h_fg), p(h_counts), p(ws), ws_bytes,
+                                    ctypes.c_void_p(up.cuda_stream) if up is not None else None)
     _cabi.check(rc, 'fo_view_transform_host')
     s.synchronize()
     assert h_counts[0].item() == len(rb) and h_counts[1].item() == len(st)
