@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
     float *pl = a.out + (int64_t)b * a.out_bstride + (int64_t)riq * V + v0;             // row riq of this sub-tile's block
     const bool staged = pa < pb || (in_range && !vec_out);
 
-    if (W == 1 && !staged) {                              // empty sub-tile: stream zeros, no staging
+    if ((W == 1 || !FO_FWD_COOP) && !staged) {            // empty sub-tile: stream zeros, no staging
         if (4 * chunk < nv) {
             float *dst = pl + 4 * chunk;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
         }
         return;
     }
-    if (W > 1 && lane == 0) s_state[warp] = !in_range ? 0 : (staged ? 2 : 1);
+    if (FO_FWD_COOP && W > 1 && lane == 0) s_state[warp] = !in_range ? 0 : (staged ? 2 : 1);
 
     if (staged) {
         int *rx = s_rx[warp];
@@ -226,7 +226,10 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
         if (cur_v >= 0) flush();
     }
 
-    if (W > 1 && vec_out) {
+#ifndef FO_FWD_COOP
+#define FO_FWD_COOP 1
+#endif
+    if (FO_FWD_COOP && W > 1 && vec_out) {
         // ---- cooperative write-out: one instruction = 4 consecutive sub-tiles x 128 B of ONE plane ----
         __syncthreads();
         const int sub = lane >> 3;                        // which of the 4 sub-tiles of a segment
