@@ -34,6 +34,9 @@ struct FwdArgs {
     const int32_t *sub_pt;
     int64_t out_bstride;            // (B,C,Z,Y,X) output: elements between samples (C_total * V; C * V when not a slice)
     int64_t out_rowstride;          // (B,Z,Y,X,C) output: elements between voxels   (C_total; C when not a slice)
+    const int32_t *sub_iv;          // heavy path: first interval of every sub-tile
+    int32_t *heavy_list;            // queue of dense sub-tiles (nullptr: everything is reduced by fwd_dense_kernel)
+    int32_t *heavy_ctl;             // [0] queue length, [1] CTAs of fwd_heavy_kernel done (both 0 between launches)
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
 };
@@ -62,59 +65,159 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 #ifndef FO_FWD_U
 #define FO_FWD_U 8
 #endif
-#ifndef FO_FWD_WARPS
-#define FO_FWD_WARPS 1
-#endif
-constexpr int kFwdWarps = FO_FWD_WARPS;     // warps (= sub-tiles) per CTA
 #ifndef FO_FWD_MIN_CTAS
-#define FO_FWD_MIN_CTAS (32 / kFwdWarps)          // <= 64 registers: 32 resident warps per SM
+#define FO_FWD_MIN_CTAS 32          // <= 64 registers: 32 single-warp CTAs per SM (the hardware's CTA limit)
 #endif
+#ifndef FO_FWD_HEAVY_PTS
+#define FO_FWD_HEAVY_PTS 256
+#endif
+constexpr int kHeavyPts   = FO_FWD_HEAVY_PTS;   // sub-tiles with more points go to the multi-warp kernel
+constexpr int kHeavyWarps = 8;
+constexpr int64_t kHeavyMaxOutBytes = 256ll << 20;   // launches writing more than this keep dense sub-tiles inline
 
-// One warp reduces one sub-tile; the kFwdWarps warps of a CTA own kFwdWarps CONSECUTIVE sub-tiles and write
-// them out TOGETHER after one barrier, so that every store instruction covers kFwdWarps*128 contiguous bytes
-// of one channel plane.  Why (profiles/micro/store_pattern.cu, B200): single-warp CTAs writing 128 B per
-// plane reach 5.9 TB/s on this tensor, CTAs writing >= 512 B per plane 6.7-6.9 TB/s (cudaMemset: 7.0).
-//
-// The dependent chain  point range -> rank records -> {depth, feature rows}  is walked with as few round
-// trips as possible: the plan's flag word and the point range are independent loads (sub-tiles per sample is
-// a kernel argument), the three record arrays are fetched together, the first group of feature rows is
-// requested before the depth values are needed.
-template <int NACC, bool EXACT, int LAYOUT>
-__global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
+// The reduction of one warp: points [p_lo, p_hi) of the sorted rank arrays, all inside one sub-tile, are
+// accumulated voxel by voxel — psum = fmaf(feat, depth, psum) from +0.0f in point order, the reference's
+// FFMA chain (bev_pool_cuda.cu:39-43) — and every finished voxel is flushed into the shared-memory stage
+// ([C][32] floats, rows rotated by (c & 7) 16-byte chunks).  lanes = channels.
+//   * the three record arrays are fetched together; the first group of feature rows is requested as soon as
+//     the row ids are there, before the (dependent) depth gather has returned;
+//   * record words / depth values are broadcast through shared memory (LDS.128, no shuffles), feature rows
+//     are fetched in groups of U with the NEXT group already in flight (2*U rows in flight per lane), and the
+//     next 32 records are fetched while a batch is processed.
+template <int NACC, bool EXACT>
+__device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, const int lane, const int p_lo,
+                                              const int p_hi, const int bV, int *rx, float *rdv,
+                                              const unsigned lane_row, const unsigned lane_rot) {
     constexpr int U = NACC <= 2 ? FO_FWD_U : 4;          // feature rows per group
-    constexpr int W = kFwdWarps;
-    extern __shared__ __align__(16) float smem[];        // W stages [C][32]
-    __shared__ __align__(16) int s_rx[W][32 + 8];        // (feature row << 5 | voxel slot) per point
-    __shared__ __align__(16) float s_rd[W][32 + 8];      // depth value per point
-    __shared__ int s_state[W];                           // 0: sub-tile out of range, 1: empty, 2: staged
+    int mx = 0, mr = -1;
+    auto load_idx = [&](int i0) {
+        mx = 0; mr = -1;
+        if (i0 + lane < p_hi) {
+            const int q = __ldg(a.rf + i0 + lane);
+            const int v = __ldg(a.rb + i0 + lane) - bV;          // sub-tiles start at multiples of 32 in a sample
+            mr = __ldg(a.rd + i0 + lane);
+            mx = (q << kSubShift) | (v & (kSub - 1));
+        }
+    };
+    load_idx(p_lo);
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    int cur_v = -1;
+    auto flush = [&]() {
+        const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+            if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
+    };
+    auto load_group = [&](float (&f)[U][NACC], int (&r)[U], int j) {
+#pragma unroll
+        for (int t = 0; t < U; ++t) r[t] = rx[j + t];
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+            const int row = (r[t] >> kSubShift) * C + lane;
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
+        }
+    };
+    auto consume = [&](const float (&f)[U][NACC], const int (&r)[U], int j, int count) {
+        float d[U];
+#pragma unroll
+        for (int t = 0; t < U; ++t) d[t] = rdv[j + t];
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+            if (t < count) {                              // warp-uniform (compile-time true for full groups)
+                const int v = r[t] & (kSub - 1);
+                if (v != cur_v) {                         // warp-uniform: a new interval starts
+                    if (cur_v >= 0) flush();
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+                    cur_v = v;
+                }
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d[t], acc[k]);
+            }
+        }
+    };
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
+    for (int i0 = p_lo; i0 < p_hi; i0 += 32) {
+        const int n = min(32, p_hi - i0);
+        __syncwarp();
+        rx[lane] = mx;
+        if (lane < 8) { rx[32 + lane] = 0; rdv[32 + lane] = 0.f; }
+        __syncwarp();
+        const int nfull = n & ~(U - 1);
+        float fa[U][NACC], fb[U][NACC];
+        int ra[U], rb2[U];
+        load_group(fa, ra, 0);                            // rows of padding records are row 0
+        rdv[lane] = md;
+        __syncwarp();
+        const bool more = i0 + 32 < p_hi;
+        if (more) load_idx(i0 + 32);                      // next batch's records fly during this batch
+        if (nfull) {
+            for (int j = 0; j < nfull; j += 2 * U) {
+                const bool has_b = j + U < nfull;
+                if (has_b) load_group(fb, rb2, j + U);
+                consume(fa, ra, j, U);
+                if (j == 0 && more) md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
+                if (has_b) {
+                    if (j + 2 * U < nfull) load_group(fa, ra, j + 2 * U);
+                    consume(fb, rb2, j + U, U);
+                }
+            }
+            if (nfull < n) {                              // remainder group
+                load_group(fa, ra, nfull);
+                consume(fa, ra, nfull, n - nfull);
+            }
+        } else {
+            consume(fa, ra, 0, n);
+        }
+    }
+    if (cur_v >= 0) flush();
+}
+
+// One warp = one sub-tile = one CTA.  The dependent chain  {flag word, point range} -> rank records ->
+// {feature rows, depth}  is three round trips: sub-tiles per sample is a kernel argument, so the plan's flag
+// word and the point range are independent loads.
+//
+// Measured on a B200 (headline shape, batch 8; profiles/r01_summary.md "second session"): this kernel wants MANY
+// SHORT-LIVED warps and a compact write window.  Runs of 2/4/8 sub-tiles per warp: 154/160/197 us; persistent
+// warps with a 4-deep software pipeline across sub-tiles: 185 us; 2/4/8-warp CTAs with a cooperative
+// >= 256-byte-per-plane write-out: 166/175/193 us; 21-25 instead of 32 resident CTAs per SM: 159-172 us;
+// write-back / .cg / .wt instead of streaming stores: 169 us; this version: 149-152 us.
+//
+// Sub-tiles with more than kHeavyPts points are not reduced here: their serial FMA chain (3 394 points at
+// 512x1408, 844 at the headline shape) is the critical path of a small launch (batch 1), so they are queued
+// for fwd_heavy_kernel, which splits a sub-tile's VOXELS over eight warps.
+template <int NACC, bool EXACT, int LAYOUT>
+__global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
+    extern __shared__ __align__(16) float smem[];        // stage [C][32]
+    __shared__ __align__(16) int s_rx[32 + 8];           // (feature row << 5 | voxel slot) per point
+    __shared__ __align__(16) float s_rd[32 + 8];         // depth value per point
+
+    const int lane = threadIdx.x;
     const int C = EXACT ? 32 * NACC : a.C;
-    // grid = (B, ceil(subs_per_sample / W)): x-fastest block order interleaves the samples, so the
-    // dense near-ego regions of all samples are reached at the same relative time
+    // grid = (B, subs_per_sample): x-fastest block order interleaves the samples, so the dense near-ego
+    // regions of all samples are reached at the same relative time
     const int sps = a.sps;
     const int b = blockIdx.x;
-    const int su = blockIdx.y * W + warp;
-    const bool in_range = su < sps;
+    const int su = blockIdx.y;
     // one round trip: the plan's flag word and the point range are independent loads
     const int flags = a.check_flags ? __ldg(&a.hdr->flags) : 0;
-    int pa = 0, pb = 0;
-    if (in_range) { pa = __ldg(a.sub_pt + b * sps + su); pb = __ldg(a.sub_pt + b * sps + su + 1); }
-    if (flags & kFlagUnsorted) return;                   // (uniform) the order-agnostic path runs instead
+    const int pa = __ldg(a.sub_pt + b * sps + su), pb = __ldg(a.sub_pt + b * sps + su + 1);
+    if (flags & kFlagUnsorted) return;                   // the order-agnostic path runs instead
     const int64_t V = a.V;
     const int bV = b * (int)V;                           // global voxel id of the sample's first voxel (< 2^31)
     const int v0 = su << kSubShift;
-    const int nv = in_range ? min(kSub, (int)V - v0) : 0;
+    const int nv = min(kSub, (int)V - v0);
     const bool vec_out = (LAYOUT == FO_LAYOUT_BCZYX) && ((V & 3) == 0);
     const int riq = lane >> 3, chunk = lane & 7;         // row within a quad of rows, 16-byte chunk
-    float *stage = smem + warp * C * kSub;
+    float *stage = smem;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
-    const unsigned lane_row = sbase + ((unsigned)lane << 7);          // byte address of row `lane`
-    const unsigned lane_rot = ((unsigned)lane & 7u) << 4;             // its rotation, in bytes
-    float *pl = a.out + (int64_t)b * a.out_bstride + (int64_t)riq * V + v0;             // row riq of this sub-tile's block
-    const bool staged = pa < pb || (in_range && !vec_out);
+    float *pl = a.out + (int64_t)b * a.out_bstride + (int64_t)riq * V + v0;      // row riq of this sub-tile's block
 
-    if ((W == 1 || !FO_FWD_COOP) && !staged) {            // empty sub-tile: stream zeros, no staging
+    if (pa >= pb && vec_out) {                            // empty sub-tile: stream zeros, no staging
         if (4 * chunk < nv) {
             float *dst = pl + 4 * chunk;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -127,130 +230,20 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
         }
         return;
     }
-    if (FO_FWD_COOP && W > 1 && lane == 0) s_state[warp] = !in_range ? 0 : (staged ? 2 : 1);
-
-    if (staged) {
-        int *rx = s_rx[warp];
-        float *rdv = s_rd[warp];
-        int mx = 0, mr = -1;
-        auto load_idx = [&](int i0) {
-            mx = 0; mr = -1;
-            if (i0 + lane < pb) {
-                const int q = __ldg(a.rf + i0 + lane);
-                const int v = __ldg(a.rb + i0 + lane) - bV;      // sub-tiles start at multiples of 32 in a sample
-                mr = __ldg(a.rd + i0 + lane);
-                mx = (q << kSubShift) | (v & (kSub - 1));
-            }
-        };
-        load_idx(pa);
-        if (EXACT) {
-#pragma unroll
-            for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
-        } else {
-            for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
-        }
-        float acc[NACC];
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-        int cur_v = -1;
-        auto flush = [&]() {
-            const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
-#pragma unroll
-            for (int k = 0; k < NACC; ++k)
-                if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
-        };
-        auto load_group = [&](float (&f)[U][NACC], int (&r)[U], int j) {
-#pragma unroll
-            for (int t = 0; t < U; ++t) r[t] = rx[j + t];
-#pragma unroll
-            for (int t = 0; t < U; ++t) {
-                const int row = (r[t] >> kSubShift) * C + lane;
-#pragma unroll
-                for (int k = 0; k < NACC; ++k) f[t][k] = (EXACT || lane + 32 * k < C) ? __ldg(a.feat + row + 32 * k) : 0.f;
-            }
-        };
-        auto consume = [&](const float (&f)[U][NACC], const int (&r)[U], int j, int count) {
-            float d[U];
-#pragma unroll
-            for (int t = 0; t < U; ++t) d[t] = rdv[j + t];
-#pragma unroll
-            for (int t = 0; t < U; ++t) {
-                if (t < count) {                          // warp-uniform (compile-time true for full groups)
-                    const int v = r[t] & (kSub - 1);
-                    if (v != cur_v) {                     // warp-uniform: a new interval starts
-                        if (cur_v >= 0) flush();
-#pragma unroll
-                        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-                        cur_v = v;
-                    }
-#pragma unroll
-                    for (int k = 0; k < NACC; ++k) acc[k] = fmaf(f[t][k], d[t], acc[k]);
-                }
-            }
-        };
-
-        float md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
-        for (int i0 = pa; i0 < pb; i0 += 32) {
-            const int n = min(32, pb - i0);
-            __syncwarp();
-            rx[lane] = mx;
-            if (lane < 8) { rx[32 + lane] = 0; rdv[32 + lane] = 0.f; }
-            __syncwarp();
-            const int nfull = n & ~(U - 1);
-            float fa[U][NACC], fb[U][NACC];
-            int ra[U], rb2[U];
-            load_group(fa, ra, 0);                        // rows of padding records are row 0
-            rdv[lane] = md;
-            __syncwarp();
-            const bool more = i0 + 32 < pb;
-            if (more) load_idx(i0 + 32);                  // next batch's records fly during this batch
-            if (nfull) {
-                for (int j = 0; j < nfull; j += 2 * U) {
-                    const bool has_b = j + U < nfull;
-                    if (has_b) load_group(fb, rb2, j + U);
-                    consume(fa, ra, j, U);
-                    if (j == 0 && more) md = (mr >= 0) ? __ldg(a.depth + mr) : 0.f;
-                    if (has_b) {
-                        if (j + 2 * U < nfull) load_group(fa, ra, j + 2 * U);
-                        consume(fb, rb2, j + U, U);
-                    }
-                }
-                if (nfull < n) {                          // remainder group
-                    load_group(fa, ra, nfull);
-                    consume(fa, ra, nfull, n - nfull);
-                }
-            } else {
-                consume(fa, ra, 0, n);
-            }
-        }
-        if (cur_v >= 0) flush();
-    }
-
-#ifndef FO_FWD_COOP
-#define FO_FWD_COOP 1
-#endif
-    if (FO_FWD_COOP && W > 1 && vec_out) {
-        // ---- cooperative write-out: one instruction = 4 consecutive sub-tiles x 128 B of ONE plane ----
-        __syncthreads();
-        const int sub = lane >> 3;                        // which of the 4 sub-tiles of a segment
-        for (int seg = 0; seg < W; seg += 4) {
-            const int w = seg + sub;
-            const int st = (w < W) ? s_state[w] : 0;
-            const int su_w = blockIdx.y * W + w;
-            const int nv_w = st ? min(kSub, (int)V - (su_w << kSubShift)) : 0;
-            const bool wr = 4 * chunk < nv_w;
-            const unsigned sw = (unsigned)__cvta_generic_to_shared(smem + w * C * kSub);
-            float *dst = a.out + (int64_t)b * a.out_bstride + ((int64_t)su_w << kSubShift) + 4 * chunk;
-            for (int c = warp; c < C; c += W) {
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (st == 2) x = lds_f4(sw + ((unsigned)c << 7) + ((unsigned)((chunk + c) & 7) << 4));
-                if (wr) __stcs(reinterpret_cast<float4 *>(dst + (int64_t)c * V), x);
-            }
-        }
+    if (a.heavy_list != nullptr && pb - pa > kHeavyPts) {     // queued for the multi-warp kernel
+        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_ctl, 1)] = b * sps + su;
         return;
     }
-    if (!staged) return;
+    if (EXACT) {
+#pragma unroll
+        for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
+    } else {
+        for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
+    }
+    reduce_points<NACC, EXACT>(a, C, lane, pa, pb, bV, s_rx, s_rd, sbase + ((unsigned)lane << 7),
+                               ((unsigned)lane & 7u) << 4);
     __syncwarp();
+
     if (LAYOUT == FO_LAYOUT_BCZYX) {
         if (vec_out) {
             // lane -> (row r of a quad, 16-byte chunk): four full 128-byte lines per instruction.  The
@@ -287,11 +280,71 @@ __global__ void __launch_bounds__(32 * kFwdWarps, FO_FWD_MIN_CTAS) fwd_dense_ker
             }
         }
     } else {
-        // (B,Z,Y,X,C): the sub-tile is nv*C contiguous floats
+        // (B,Z,Y,X,C): the sub-tile is nv rows of C floats
         float *dst = a.out + ((int64_t)bV + v0) * a.out_rowstride;
         for (int e = lane; e < nv * C; e += 32) {
             const int v = e / C, c = e - v * C;
             __stcs(dst + (int64_t)v * a.out_rowstride + c, stage[stage_index(c, v)]);
+        }
+    }
+}
+
+// Dense sub-tiles (> kHeavyPts points): one CTA of kHeavyWarps warps per queued sub-tile.  The sub-tile's
+// intervals (<= 32, one per occupied voxel) are split into kHeavyWarps contiguous groups of about equal point
+// count; every warp reduces its group into the CTA's shared stage (distinct voxel columns), then the block is
+// written out by all warps.  Only the (B,C,Z,Y,X) layout with V % 4 == 0 queues sub-tiles.  The last CTA to
+// finish re-arms the queue for the next launch: a plan serves one forward launch at a time.
+template <int NACC, bool EXACT>
+__global__ void __launch_bounds__(32 * kHeavyWarps) fwd_heavy_kernel(FwdArgs a) {
+    extern __shared__ __align__(16) float smem[];        // stage [C][32], shared by the CTA
+    __shared__ __align__(16) int s_rx[kHeavyWarps][32 + 8];
+    __shared__ __align__(16) float s_rd[kHeavyWarps][32 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = EXACT ? 32 * NACC : a.C;
+    const int n_heavy = *a.heavy_ctl;
+    const int sps = a.sps;
+    const int64_t V = a.V;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const int u = a.heavy_list[h];
+        const int b = u / sps, su = u - b * sps;
+        const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
+        const int ia = __ldg(a.sub_iv + u), ni = min(__ldg(a.sub_iv + u + 1) - ia, kSub);
+        const int v0 = su << kSubShift;
+        const int nv = min(kSub, (int)V - v0);
+        for (int e = threadIdx.x; e < C * (kSub / 4); e += 32 * kHeavyWarps) sts_zero4(sbase + 16u * e);
+        // this warp's intervals: those whose first point falls into the warp's share of [pa, pb)
+        const int s_l = (lane < ni) ? __ldg(a.starts + ia + lane) : pb;
+        const int share = ((long long)(s_l - pa) * kHeavyWarps) / (pb - pa);
+        const unsigned mine = __ballot_sync(0xffffffffu, lane < ni && share == warp);
+        int p_lo = 0, p_hi = 0;
+        if (mine) {
+            const int first = __ffs(mine) - 1, last = 31 - __clz(mine);
+            p_lo = __shfl_sync(0xffffffffu, s_l, first);
+            p_hi = __shfl_sync(0xffffffffu, s_l, min(last + 1, 31));
+            if (last + 1 >= ni) p_hi = pb;
+        }
+        __syncthreads();                                  // the stage is zeroed
+        if (mine)
+            reduce_points<NACC, EXACT>(a, C, lane, p_lo, p_hi, b * (int)V, s_rx[warp], s_rd[warp],
+                                       sbase + ((unsigned)lane << 7), ((unsigned)lane & 7u) << 4);
+        __syncthreads();
+        // write-out: lane -> (row of a quad, 16-byte chunk); quads of rows are dealt to the warps
+        const int riq = lane >> 3, chunk = lane & 7;
+        float *blk = a.out + (int64_t)b * a.out_bstride + v0;
+        for (int r = 4 * warp + riq; r < C; r += 4 * kHeavyWarps) {
+            const int ck = (chunk - r) & 7;               // logical chunk held at smem position `chunk` of row r
+            const float4 x = lds_f4(sbase + ((unsigned)r << 7) + 16u * chunk);
+            if (4 * ck < nv) __stcs(reinterpret_cast<float4 *>(blk + (int64_t)r * V + 4 * ck), x);
+        }
+        __syncthreads();                                  // the stage is reused by the next queued sub-tile
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.heavy_ctl + 1, 1) == (int)gridDim.x - 1) {
+            a.heavy_ctl[0] = 0;
+            a.heavy_ctl[1] = 0;
+            __threadfence();
         }
     }
 }
@@ -360,8 +413,15 @@ template <int NACC, bool EXACT, int LAYOUT>
 int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(a.B, n_ctas), 32 * kFwdWarps, smem, stream>>>(a);
+    kern<<<dim3(a.B, n_ctas), 32, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
+    if (a.heavy_list != nullptr) {
+        auto heavy = fwd_heavy_kernel<NACC, EXACT>;
+        if (smem > 48 * 1024)
+            FO_CUDA(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heavy<<<2 * sm_count(), 32 * kHeavyWarps, smem, stream>>>(a);
+        FO_LAUNCH_CHECK("fwd_heavy_kernel");
+    }
     return FO_OK;
 }
 template <int LAYOUT>
@@ -418,9 +478,18 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     a.out_rowstride = c_total;
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
-    const size_t smem = (size_t)kFwdWarps * kSub * c * sizeof(float);
+    // dense sub-tiles are queued for the multi-warp kernel when the block can be written with 128-bit stores
+    // ... and when the launch is short enough for one dense sub-tile's serial chain to be its critical path
+    // (measured: batch 1 forward 50 -> 37 us at the headline shape, 273 -> 133 us at 512x1408 / C = 80; at batch 8
+    // the chain hides among 160 000 other sub-tiles and the extra launch costs 11 us)
+    const bool heavy_ok = out_layout == FO_LAYOUT_BCZYX && (n_vox & 3) == 0 && interval_starts != nullptr &&
+                          (int64_t)B * n_vox * c * 4 <= kHeavyMaxOutBytes;
+    a.sub_iv = pv.sub_iv;
+    a.heavy_list = heavy_ok ? pv.heavy_list : nullptr;
+    a.heavy_ctl = const_cast<FwdPlanHeader *>(pv.hdr)->fwd_heavy;
+    const size_t smem = (size_t)kSub * c * sizeof(float);
     // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
-    const int n_ctas = (sps + kFwdWarps - 1) / kFwdWarps;            // per sample (grid.y)
+    const int n_ctas = sps;                                           // per sample (grid.y)
     const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas <= 65535 && B <= 65535;
     if (dense_ok) {
         int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
@@ -483,5 +552,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
     a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
+    a.sub_iv = nullptr; a.heavy_list = nullptr; a.heavy_ctl = nullptr;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

@@ -50,7 +50,8 @@ struct __align__(16) FwdPlanHeader {
     int32_t subs_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
     int32_t structured;      // 1: pt2vox / vox2iv are valid (plan produced by fo_rank_prepare)
-    int32_t reserved[11];
+    int32_t fwd_heavy[2];    // forward: queue length of dense sub-tiles, heavy-kernel CTAs done (0 between launches)
+    int32_t reserved[9];
 };
 static_assert(sizeof(FwdPlanHeader) == 64, "header is one 64-byte block");
 
@@ -67,9 +68,10 @@ __host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vo
 
 // ----------------------------------------------------------------------------------------------
 // Forward plan buffer:
-//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | vox2iv[NV] | pos2iv[P_cap] | pt2vox[P_cap] | iv_vox[IV_cap]]
+//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | vox2iv[NV] | pos2iv[P_cap] | pt2vox[P_cap] | iv_vox[IV_cap]]
 //   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
 //   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
+//   heavy_list[]  per-launch queue of the forward: sub-tiles with more than 256 points
 //   vox2iv[v]     interval id of voxel v (rows of the backward's gathered out_grad); only when hdr.structured
 //   pos2iv[i]     interval id of sorted position i; only for plans built from caller-supplied intervals
 //   pt2vox[p]     voxel id of frustum point p, -1 if filtered; only when hdr.structured
@@ -83,6 +85,7 @@ struct FwdPlanView {
     FwdPlanHeader *hdr;
     int32_t *sub_iv;
     int32_t *sub_pt;
+    int32_t *heavy_list;
     int32_t *vox2iv;
     int32_t *pos2iv;
     int32_t *iv_vox;
@@ -96,13 +99,13 @@ __host__ inline size_t fwd_plan_sub_bytes(int64_t n_vox_total) {
 }
 __host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
     const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
-    return 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv + 8 * pc + 4 * (pc < nv ? pc : nv));
+    return 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv + 8 * pc + 4 * (pc < nv ? pc : nv));
 }
 // The layout is a pure function of (n_vox_total, plan_bytes): every entry point is handed the same
 // plan_bytes the buffer was sized with and recovers the same pointers without reading the device.
 __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_bytes, FwdPlanView *v) {
     const int64_t nv = align_up(n_vox_total, 64);
-    const size_t fixed = 256 + 2 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv);
+    const size_t fixed = 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv);
     if (plan_bytes < fixed + 64 * 12) return false;
     const int64_t rest = (int64_t)(plan_bytes - fixed);
     int64_t pc = rest / 12;
@@ -112,6 +115,7 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
     v->hdr = (FwdPlanHeader *)p;             p += 256;
     v->sub_iv = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->sub_pt = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
+    v->heavy_list = (int32_t *)p;            p += fwd_plan_sub_bytes(n_vox_total);
     v->vox2iv = (int32_t *)p;                p += nv * 4;
     v->pos2iv = (int32_t *)p;                p += pc * 4;
     v->pt2vox = (int32_t *)p;                p += pc * 4;
@@ -194,6 +198,15 @@ int set_error(int code, const char *fmt, ...);
 // opens + validates a forward plan buffer (defined in rank_prepare.cu)
 int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
                         FwdPlanView *pv, int64_t *n_subs, int *sps);
+
+// number of SMs of the current device (148 on B200)
+inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+        n = 148;
+    return n;
+}
 
 inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
     int64_t b = (work_items + per_block - 1) / per_block;
