@@ -36,6 +36,7 @@ struct FwdArgs {
     int64_t out_rowstride;          // (B,Z,Y,X,C) output: elements between voxels   (C_total; C when not a slice)
     const int32_t *sub_iv;          // heavy path: first interval of every sub-tile
     int32_t *heavy_list;            // queue of dense sub-tiles (nullptr: everything is reduced by fwd_dense_kernel)
+    int32_t heavy_pts;              // sub-tiles with more points are queued
     int32_t *heavy_ctl;             // [0] queue length, [1] CTAs of fwd_heavy_kernel done (both 0 between launches)
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
@@ -71,9 +72,12 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 #ifndef FO_FWD_HEAVY_PTS
 #define FO_FWD_HEAVY_PTS 256
 #endif
-constexpr int kHeavyPts   = FO_FWD_HEAVY_PTS;   // sub-tiles with more points go to the multi-warp kernel
+constexpr int kHeavyPts   = FO_FWD_HEAVY_PTS;   // short launches: sub-tiles with more points go to the multi-warp kernel
 constexpr int kHeavyWarps = 8;
-constexpr int64_t kHeavyMaxOutBytes = 256ll << 20;   // launches writing more than this keep dense sub-tiles inline
+#ifndef FO_FWD_HEAVY_MAX_MB
+#define FO_FWD_HEAVY_MAX_MB 256
+#endif
+constexpr int64_t kHeavyMaxOutBytes = (int64_t)FO_FWD_HEAVY_MAX_MB << 20;   // larger launches keep dense sub-tiles inline
 
 // The reduction of one warp: points [p_lo, p_hi) of the sorted rank arrays, all inside one sub-tile, are
 // accumulated voxel by voxel — psum = fmaf(feat, depth, psum) from +0.0f in point order, the reference's
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
         }
         return;
     }
-    if (a.heavy_list != nullptr && pb - pa > kHeavyPts) {     // queued for the multi-warp kernel
+    if (a.heavy_list != nullptr && pb - pa > a.heavy_pts) {   // queued for the multi-warp kernel
         if (lane == 0) a.heavy_list[atomicAdd(a.heavy_ctl, 1)] = b * sps + su;
         return;
     }
@@ -479,11 +483,16 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
     // dense sub-tiles are queued for the multi-warp kernel when the block can be written with 128-bit stores
-    // ... and when the launch is short enough for one dense sub-tile's serial chain to be its critical path
-    // (measured: batch 1 forward 50 -> 37 us at the headline shape, 273 -> 133 us at 512x1408 / C = 80; at batch 8
-    // the chain hides among 160 000 other sub-tiles and the extra launch costs 11 us)
-    const bool heavy_ok = out_layout == FO_LAYOUT_BCZYX && (n_vox & 3) == 0 && interval_starts != nullptr &&
-                          (int64_t)B * n_vox * c * 4 <= kHeavyMaxOutBytes;
+    // ... and when a dense sub-tile's serial chain can be the launch's critical path: short launches (threshold 256
+    // points), or geometries with at least one frustum point per voxel on average (threshold 1024).  Measured on a
+    // B200 (us, inline -> queued): headline shape batch 1 / 2: 50 -> 37 / 67 -> 52; 512x1408 C = 32 batch 8:
+    // 398 -> 315; 512x1408 D = 118 C = 80 batch 1 / 2 / 8: 261 -> 128 / 328 -> 196 / 716 -> 627; at the headline
+    // shape, batch 8, the chains hide among 160 000 other sub-tiles and the second launch would cost 3-8 us.
+    const bool vec_ok = out_layout == FO_LAYOUT_BCZYX && (n_vox & 3) == 0 && interval_starts != nullptr;
+    const bool short_launch = (int64_t)B * n_vox * c * 4 <= kHeavyMaxOutBytes;
+    const bool dense_geometry = n_points >= (int64_t)B * n_vox;
+    const bool heavy_ok = vec_ok && (short_launch || dense_geometry);
+    a.heavy_pts = short_launch ? kHeavyPts : 4 * kHeavyPts;
     a.sub_iv = pv.sub_iv;
     a.heavy_list = heavy_ok ? pv.heavy_list : nullptr;
     a.heavy_ctl = const_cast<FwdPlanHeader *>(pv.hdr)->fwd_heavy;
@@ -552,6 +561,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
     a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
-    a.sub_iv = nullptr; a.heavy_list = nullptr; a.heavy_ctl = nullptr;
+    a.sub_iv = nullptr; a.heavy_list = nullptr; a.heavy_ctl = nullptr; a.heavy_pts = INT_MAX;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }
