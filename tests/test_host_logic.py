@@ -129,3 +129,74 @@ def test_bench_byte_model_matches_baseline_md():
     ab = bench.algorithmic_bytes(1, 6, 88, 16, 44, 32, 640000, 211434, 138852)
     assert round(ab['fwd'] / 1e6, 2) == 87.60 and round(ab['bwd'] / 1e6, 2) == 24.40
     assert round(ab['pre'] / 1e6, 2) == 8.11 and round(ab['total'] / 1e6, 2) == 120.10
+
+
+def test_new_entry_points_have_no_cpu_path():
+    """Sibling ops, the channel-slice op and the fused-geometry precompute raise on CPU tensors too."""
+    from fusionocc_b200 import bev_pool_v2_cat, pack_calibration, rank_prepare_calib
+    from fusionocc_b200.pool_v1 import bev_pool, occ_pool, rank_from_keys
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match='CUDA'):
+        bev_pool(z(4, 8), z(4, 4).int(), 1, 1, 2, 2)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        occ_pool(z(4, 8), z(4, 4).int(), 1, 1, 2, 2)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        rank_from_keys(z(4).int(), 8)
+    frame = (z(1, 1, 2, 2, 2), z(1, 1, 2, 2, 4), z(1).int(), z(1).int(), z(1).int(), z(1).int(), z(1).int())
+    with pytest.raises(RuntimeError, match='CUDA'):
+        bev_pool_v2_cat([frame, frame], (1, 1, 2, 2, 4))
+    with pytest.raises(ValueError):
+        bev_pool_v2_cat([], (1, 1, 2, 2, 4))
+    sh, vt = _vt('tiny')
+    cal = make_calibration(sh, 1)
+    cam, bda12, has_t = pack_calibration(cal[0], cal[2], cal[3], cal[4], cal[5])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        rank_prepare_calib(vt.frustum, cam, bda12, has_t, 1, sh.n_cams, [0, 0, 0], [1, 1, 1], [4, 4, 4])
+
+
+def test_pack_calibration_layout_and_formula():
+    """cam_mats / bda12 are the matrices of view_transformer.py:161-172; evaluating the per-point formula with
+    them in fp64 reproduces the oracle's get_lidar_coor to fp32 rounding (3x3 and 4x4 bda)."""
+    from fusionocc_b200 import pack_calibration
+    from oracle import rank_oracle as ro
+    sh, vt = _vt('tiny')
+    B = 2
+    s2e, e2g, k, pr, pt, bda = make_calibration(sh, B, frame_shift=True)
+    for use_bda4 in (False, True):
+        b_in = bda
+        if use_bda4:
+            b_in = torch.eye(4).repeat(B, 1, 1)
+            b_in[:, :3, :3] = bda * 1.02
+            b_in[:, :3, 3] = torch.tensor([0.25, -0.5, 0.125])
+        cam, bda12, has_t = pack_calibration(s2e, k, pr, pt, b_in)
+        N = s2e.shape[1]
+        assert cam.shape == (B * N, 24) and bda12.shape == (B, 12) and has_t == use_bda4
+        assert torch.equal(cam[:, :9].reshape(B, N, 3, 3), torch.inverse(pr))
+        assert torch.equal(cam[:, 9:12].reshape(B, N, 3), pt)
+        assert torch.equal(cam[:, 21:24].reshape(B, N, 3), s2e[:, :, :3, 3])
+        fr = vt.frustum.double()                                   # (D,H,W,3)
+        c = cam.double().reshape(B, N, 24)
+        p = fr[None, None] - c[:, :, None, None, None, 9:12]
+        p = torch.einsum('bnij,bndhwj->bndhwi', c[..., :9].reshape(B, N, 3, 3), p)
+        p = torch.cat((p[..., :2] * p[..., 2:3], p[..., 2:3]), -1)
+        p = torch.einsum('bnij,bndhwj->bndhwi', c[..., 12:21].reshape(B, N, 3, 3), p) + c[:, :, None, None, None, 21:24]
+        bd = bda12.double()
+        p = torch.einsum('bij,bndhwj->bndhwi', bd[:, :9].reshape(B, 3, 3), p) + bd[:, None, None, None, None, 9:12]
+        want = vt.get_lidar_coor(s2e, e2g, k, pr, pt, b_in)
+        assert torch.allclose(p.float(), want, rtol=1e-5, atol=1e-4)
+        if not use_bda4:
+            ref = ro.get_lidar_coor(ro.create_frustum(sh.depth_cfg, sh.input_size, sh.downsample), s2e, e2g, k, pr, pt, bda)
+            assert torch.allclose(p.float(), ref, rtol=1e-5, atol=1e-4)
+
+
+def test_overlay_import_paths_sibling_ops():
+    """overlay/projects/{BEVFusion,CONet} keep the sibling ops' module layout (bev_pool.py:85, OCC_Pool.py:74)."""
+    import importlib.util
+    import fusionocc_b200.pool_v1 as pv1
+    for rel, name in ((('projects', 'BEVFusion', 'bevfusion', 'ops', 'bev_pool', 'bev_pool.py'), 'bev_pool'),
+                      (('projects', 'CONet', 'mmdet3d_plugin', 'ops', 'occ_pooling', 'OCC_Pool.py'), 'occ_pool')):
+        p = os.path.join(ROOT, 'overlay', *rel)
+        spec = importlib.util.spec_from_file_location('overlay_' + name, p)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert getattr(mod, name) is getattr(pv1, name)
