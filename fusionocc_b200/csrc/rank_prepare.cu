@@ -289,16 +289,69 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     }
 }
 
-// Same job with a bitonic network over packed 32-bit keys (voxel id << 7 | depth bin): 25 shuffle stages x R
-// registers instead of 32 x R broadcasts x R compares.  Needs B*Z*Y*X < 2^24 and D <= 128.
+// Same job with a bitonic network over packed 32-bit keys (voxel id << 7 | depth bin).  Needs B*Z*Y*X < 2^24
+// and D <= 128.  Only ~57 % of a pixel's depth bins land inside the grid, so the valid keys are first COMPACTED
+// (ballot + popc through a per-warp shared-memory row) and the network is sized to the live count: 32 / 64 / 128
+// elements = 15 / 21x2 / 28x4 compare-exchange steps (the kernel is issue-bound: 34 -> 2x us at the headline shape).
+template <int RS>   // ascending bitonic sort of 32*RS keys, element e = 32 r + lane
+__device__ __forceinline__ void bitonic_sort_regs(int (&key)[RS], const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * RS; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {                               // partner in another register of the same lane
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const int pr = r ^ (j >> 5);
+                    if (pr > r) {
+                        const bool up = (((32 * r) & k) == 0);
+                        const int lo = min(key[r], key[pr]), hi = max(key[r], key[pr]);
+                        key[r] = up ? lo : hi;
+                        key[pr] = up ? hi : lo;
+                    }
+                }
+            } else {                                     // partner in lane ^ j, same register
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const int other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                    const bool up = ((((32 * r) | lane) & k) == 0);
+                    const bool lower = (lane & j) == 0;
+                    key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                }
+            }
+        }
+    }
+}
+
+template <int RS>
+__device__ __forceinline__ void plan_sort_emit(const int *cmp, const int n, const int lane, const int ebase,
+                                               const int pbase, const int HW, const int32_t *__restrict__ vox2iv,
+                                               int32_t *ent_p, int32_t *ent_iv) {
+    int key[RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) key[r] = (32 * r + lane < n) ? cmp[32 * r + lane] : INT_MAX;
+    bitonic_sort_regs<RS>(key, lane);
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+        const int e = 32 * r + lane;
+        if (e < n) {
+            ent_p[ebase + e] = pbase + (key[r] & 127) * HW;
+            ent_iv[ebase + e] = __ldg(vox2iv + (key[r] >> 7));
+        }
+    }
+}
+
 template <int R>   // R in {1, 2, 4}: 32 * R >= D
 __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     const int32_t *__restrict__ pt2vox, const int32_t *__restrict__ vox2iv, int D, int HW, int n_rows,
     BwdPlanHeader *hdr, int32_t *ent_p, int32_t *ent_iv, int32_t *starts, int32_t *lengths, int32_t *ids,
     const int32_t *n_points_dev) {
+    __shared__ int s_cmp[8][32 * R];
     const int lane = threadIdx.x & 31;
+    int *cmp = s_cmp[threadIdx.x >> 5];
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
@@ -309,53 +362,28 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
         int key[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int d = lane + 32 * r;                 // element index e = 32 r + lane holds depth bin d = e
-            key[r] = INT_MAX;
+            const int d = lane + 32 * r;
+            key[r] = -1;
             if (d < D) {
                 const int v = __ldg(pt2vox + pbase + d * HW);
                 if (v >= 0) key[r] = (v << 7) | d;
             }
         }
-        // bitonic sort, ascending, over n = 32 R elements; element e = 32 r + lane
-#pragma unroll
-        for (int k = 2; k <= 32 * R; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j >= 32) {                           // partner in another register of the same lane
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int pr = r ^ (j >> 5);
-                        if (pr > r) {
-                            const bool up = (((32 * r) & k) == 0);
-                            const int lo = min(key[r], key[pr]), hi = max(key[r], key[pr]);
-                            key[r] = up ? lo : hi;
-                            key[pr] = up ? hi : lo;
-                        }
-                    }
-                } else {                                 // partner in lane ^ j, same register
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int other = __shfl_xor_sync(0xffffffffu, key[r], j);
-                        const bool up = ((((32 * r) | lane) & k) == 0);
-                        const bool lower = (lane & j) == 0;
-                        key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
-                    }
-                }
-            }
-        }
-        int cnt = 0;
+        int n = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (key[r] != INT_MAX) {
-                const int e = 32 * r + lane;
-                ent_p[q * D + e] = pbase + (key[r] & 127) * HW;
-                ent_iv[q * D + e] = __ldg(vox2iv + (key[r] >> 7));
-                ++cnt;
-            }
+            const unsigned m = __ballot_sync(0xffffffffu, key[r] >= 0);
+            if (key[r] >= 0) cmp[n + __popc(m & lt)] = key[r];
+            n += __popc(m);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) { starts[q] = q * D; lengths[q] = cnt; ids[q] = q; }
+        __syncwarp();
+        if (n > 0) {
+            if (n <= 32) plan_sort_emit<1>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
+            else if (R >= 2 && n <= 64) plan_sort_emit<(R >= 2 ? 2 : 1)>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
+            else plan_sort_emit<R>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
+        }
+        if (lane == 0) { starts[q] = q * D; lengths[q] = n; ids[q] = q; }
+        __syncwarp();                                    // the compaction row is reused by the next pixel
     }
 }
 
