@@ -474,6 +474,20 @@ def run_ours(args):
                         '(bit-identical to the torch ops, matvec_mode 3), never stored; not part of value'}
     ns.rank_prepare()
 
+    # ---- row (f-2): the step before the splat, one native pass vs the reference's torch ops
+    from fusionocc_b200 import lift_prepare
+    lift = {}
+    for dt, nm in ((torch.float32, 'f32'), (torch.float16, 'f16')):
+        xl = torch.randn(B * ns.N, ns.D + ns.C, ns.H, ns.W, device=dev).to(dt)
+
+        def ref_ops():
+            d = xl[:, :ns.D].float().softmax(dim=1)                              # view_transformer.py:333-335
+            f = xl[:, ns.D:ns.D + ns.C].permute(0, 2, 3, 1).contiguous().float()   # bev_pool.py:20-21
+            return d, f
+        lift[nm] = {'torch_ops_ms': timed(ref_ops), 'lift_prepare_ms': timed(lambda: lift_prepare(xl, ns.D, ns.C))}
+        del xl
+    lift['note'] = 'depth softmax + channel split + NCHW->NHWC + fp32 cast of the depth-net output; not part of value'
+
     # ---- e2e through the host-buffer entry
     hs = HostStep(ns, n_chunks=args.e2e_chunks)
     for _ in range(2):
@@ -565,6 +579,7 @@ def run_ours(args):
     if cpu:
         line['cpu_baseline'] = cpu
     line['geometry'] = geometry
+    line['lift_prepare'] = lift
     if gather:
         line['gather'] = gather
     print(json.dumps(line))

@@ -60,6 +60,10 @@ SIGNATURES = {
     'fo_rank_from_keys_scratch_bytes': (c_size_t, [c_int64, c_int64]),
     'fo_rank_from_keys': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_size_t]),
+    'fo_lift_prepare_forward': (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_void_p]),
+    'fo_lift_prepare_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                         c_int32, c_void_p, c_int32]),
     'fo_compat_bev_pool_v2': (None, [c_int, c_int] + [c_void_p] * 8),
     'fo_compat_bev_pool_v2_grad': (None, [c_int, c_int] + [c_void_p] * 10),
     'fo_view_transform_host_workspace_bytes': (c_size_t, [c_int32] * 10),

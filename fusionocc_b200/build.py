@@ -20,7 +20,7 @@ LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libfusionocc_b200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-SOURCES = ['cabi.cu', 'rank_prepare.cu', 'bev_pool_fwd.cu', 'bev_pool_bwd.cu']
+SOURCES = ['cabi.cu', 'rank_prepare.cu', 'bev_pool_fwd.cu', 'bev_pool_bwd.cu', 'lift_prepare.cu']
 HEADERS = ['common.cuh', 'bucket_sort.cuh']
 
 NVCC_FLAGS = [

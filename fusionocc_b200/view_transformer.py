@@ -158,10 +158,14 @@ class LSSViewTransformer(_Base):
     ``fuse_geometry`` (default False) — the non-accelerated ``view_transform`` never materialises the
     (B,N,D,H,W,3) frustum points: ``get_lidar_coor`` + ``voxel_pooling_prepare_v2`` run as ONE native call
     (fo_rank_prepare_calib).  Implies the sync-free output contract.
+    ``fuse_lift`` (default False) — ``forward`` runs the depth softmax, the channel split, the NCHW->NHWC
+    transpose and the fp32 cast of the depth-net output as ONE native pass (``lift_prepare``)
+    instead of :333-335 + the transpose copy of bev_pool.py:20-21; softmax within rtol 1e-5 of torch's.
     """
 
     def __init__(self, grid_config, input_size, downsample=16, in_channels=512, out_channels=64,
-                 accelerate=False, sid=False, collapse_z=True, sync_free=False, fuse_geometry=False):
+                 accelerate=False, sid=False, collapse_z=True, sync_free=False, fuse_geometry=False,
+                 fuse_lift=False):
         super().__init__()
         self.grid_config = grid_config
         self.downsample = downsample
@@ -176,6 +180,7 @@ class LSSViewTransformer(_Base):
         self.collapse_z = collapse_z
         self.sync_free = sync_free
         self.fuse_geometry = fuse_geometry
+        self.fuse_lift = fuse_lift
         self._accel_plan: Optional[VoxelPoolPlan] = None
 
     # ------------------------------------------------------------------ a1 (:87-103)
@@ -339,6 +344,10 @@ class LSSViewTransformer(_Base):
         B, N, C, H, W = x.shape
         x = x.view(B * N, C, H, W)
         x = self.depth_net(x)
+        if self.fuse_lift:                       # softmax + split + NHWC transpose + fp32 cast in one native pass
+            from .lift import lift_prepare
+            depth, feat_nhwc = lift_prepare(x, self.D, self.out_channels)
+            return self.view_transform(input, depth, feat_nhwc.permute(0, 3, 1, 2))
         depth_digit = x[:, :self.D, ...]
         tran_feat = x[:, self.D:self.D + self.out_channels, ...]
         depth = depth_digit.softmax(dim=1)

@@ -57,6 +57,11 @@ extern "C" {
 #define FO_LAYOUT_BCZYX  0   /* contiguous (B,C,Z,Y,X): what bev_pool_v2() returns (bev_pool.py:91)      */
 #define FO_LAYOUT_BZYXC  1   /* contiguous (B,Z,Y,X,C): what the reference extension itself writes/reads */
 
+/* Element type of a tensor passed as void* (fo_lift_prepare_*). */
+#define FO_DTYPE_F32   0
+#define FO_DTYPE_F16   1
+#define FO_DTYPE_BF16  2
+
 typedef void *fo_stream_t;   /* cudaStream_t */
 
 int         fo_abi_version(void);
@@ -259,6 +264,27 @@ int fo_rank_from_keys(fo_stream_t stream, const int32_t *keys, int64_t n_points,
                       int32_t *sorted_keys, int32_t *order,
                       int32_t *interval_starts, int32_t *interval_lengths, int32_t *counts_dev,
                       void *scratch, size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * The step before the splat: depth softmax + channel split + NCHW -> NHWC transpose +
+ * fp16/bf16 -> fp32 conversion of the depth-net output in one pass.  Replaces view_transformer.py:329-336
+ * (x[:, :D].softmax(dim=1), x[:, D:D+C]) and the feat.contiguous().float() transpose copy of bev_pool.py:20-21.
+ *
+ *   x            (BN, c_in, H*W) contiguous, element type x_dtype; channels [0,D) depth logits,
+ *                [D, D+C) context features, [D+C, c_in) ignored
+ *   depth        fp32 (BN, D, H*W): softmax over D, computed in fp32 as exp(x - max) / sum
+ *   feat_nhwc    fp32 (BN, H*W, C): the rows bev_pool_v2 gathers (ranks_feat index them)
+ * Backward: x_grad[:, :D] = (depth_grad - sum_d(depth_grad * depth)) * depth (softmax Jacobian),
+ * x_grad[:, D:D+C] = feat_nhwc_grad transposed back, x_grad[:, D+C:] = 0; x_grad has x's shape and dtype.
+ * ------------------------------------------------------------------------------------------------ */
+int fo_lift_prepare_forward(fo_stream_t stream, const void *x, int32_t x_dtype,
+                            int64_t BN, int32_t c_in, int32_t D, int32_t C, int32_t HW,
+                            float *depth, float *feat_nhwc);
+
+int fo_lift_prepare_backward(fo_stream_t stream, const float *depth, const float *depth_grad,
+                             const float *feat_nhwc_grad,
+                             int64_t BN, int32_t c_in, int32_t D, int32_t C, int32_t HW,
+                             void *x_grad, int32_t x_dtype);
 
 /* ------------------------------------------------------------------------------------------------
  * Source-compatible L0 symbols.  Same C signatures, semantics (assign into a caller-zeroed
