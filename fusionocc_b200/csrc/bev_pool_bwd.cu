@@ -21,6 +21,7 @@ struct GatherArgs {
     const float *og;                // (B,C,Z,Y,X), possibly a channel slice of a wider tensor
     int64_t og_bstride;             // elements between samples
     int32_t C;
+    int32_t sps;                    // sub-tiles per sample
     int64_t V;
     const FwdPlanHeader *hdr;
     const int32_t *sub_iv;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kThreads) bwd_gather_kernel(GatherArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = EXACT ? 32 * NACC : a.C;
-    const int sps = a.hdr->subs_per_sample;
+    const int sps = a.sps;                     // kernel argument: one dependent load less per CTA
     const int b = blockIdx.x;
     const int su = blockIdx.y * kWarpsPerCta + warp;
     if (su >= sps) return;
@@ -422,6 +423,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
         GatherArgs ga;
         ga.og = out_grad + (int64_t)c_offset * n_vox; ga.og_bstride = (int64_t)c_total * n_vox; ga.C = c; ga.V = n_vox;
+        ga.sps = sps;
         ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
         const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
         if (n_ctas > 65535 || B > 65535 || c > 256)

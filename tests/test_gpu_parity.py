@@ -480,6 +480,27 @@ def test_invalid_arguments_raise():
     rc = lib.fo_bev_pool_v2_forward(None, 0, None, None, None, None, None, None, None, 0, 0, None, 1, 1, None, 0, 0,
                                     None, 0)
     assert rc == 1 and b'channels' in lib.fo_last_error()
+    # the entry points added for rows f-1 .. f-4 validate their arguments the same way
+    rc = lib.fo_bev_pool_v2_forward_slice(None, 8, None, None, None, None, None, None, None, 0, 0, None, 1, 64, None,
+                                          0, 12, 6, 0, None, 0)
+    assert rc == 1 and b'slice' in lib.fo_last_error()
+    rc = lib.fo_bev_pool_v2_backward_slice(None, 8, None, 0, 4, 0, None, None, 0, 0, 1, 64, 0, 1, None, None, None, 0,
+                                           None, 0, None, 0)
+    assert rc == 1 and b'slice' in lib.fo_last_error()
+    f3 = _cabi.f3([0, 0, 0])
+    rc = lib.fo_rank_prepare_calib(None, None, None, None, 0, 3, None, 1, 1, 1, 1, 1, f3, f3, 1, 1, 1, None, None, None,
+                                   None, None, None, None, 0, None, 0)
+    assert rc == 1 and b'calibration' in lib.fo_last_error()
+    fr = z(3)
+    rc = lib.fo_rank_prepare_calib(None, fr.data_ptr(), fr.data_ptr(), fr.data_ptr(), 0, 7, None, 1, 1, 1, 1, 1, f3, f3,
+                                   1, 1, 1, None, None, None, None, None, None, None, 0, None, 0)
+    assert rc == 1 and b'matvec_mode' in lib.fo_last_error()
+    rc = lib.fo_rank_from_keys(None, None, 5, 0, None, None, None, None, None, None, 0)
+    assert rc == 1
+    rc = lib.fo_lift_prepare_forward(None, fr.data_ptr(), 9, 1, 4, 2, 2, 4, None, None)
+    assert rc == 1 and b'dtype' in lib.fo_last_error()
+    rc = lib.fo_lift_prepare_forward(None, fr.data_ptr(), 0, 1, 3, 2, 2, 4, None, None)
+    assert rc == 1 and b'sizes' in lib.fo_last_error()
 
 
 def test_size_independent_properties_at_full_size():
