@@ -32,7 +32,8 @@ constexpr int kScanTile    = kScanThreads * kScanItems;   // 2048 buckets per CT
 // agg[0..t).  (Tried and rejected, profiles/r01: a decoupled look-back scan, 41 us, and aggregating with
 // one atomic per element inside the count pass, 157 us of same-address contention.)
 __global__ void __launch_bounds__(kScanThreads) tile_reduce_kernel(const int32_t *__restrict__ cnt, int64_t n_buckets,
-                                                                   unsigned long long *__restrict__ agg) {
+                                                                   unsigned long long *__restrict__ agg,
+                                                                   unsigned long long *__restrict__ agg_group) {
     __shared__ unsigned long long s_red[kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * kScanTile;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kScanThreads) tile_reduce_kernel(const int32_t
 #pragma unroll
         for (int w = 0; w < kScanThreads / 32; ++w) t += s_red[w];
         agg[blockIdx.x] = t;
+        atomicAdd(agg_group + blockIdx.x / kScanGroup, t);   // ~kScanGroup adds per address: no contention
     }
 }
 
@@ -78,7 +80,8 @@ struct ScanArgs {
     int32_t  n_subs;
     FwdPlanHeader *fwd_hdr;  // may be nullptr
     BwdPlanHeader *bwd_hdr;  // may be nullptr
-    const unsigned long long *agg;   // [ceil(n_buckets / kScanTile)] from the count pass
+    const unsigned long long *agg;   // [ceil(n_buckets / kScanTile)] from the reduce pass
+    const unsigned long long *agg_group;   // sums over groups of kScanGroup tiles
 };
 
 // One CTA = kScanTile consecutive buckets.
@@ -89,9 +92,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
     const int tile = blockIdx.x;
     const int64_t base = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
 
-    // exclusive prefix of this tile = sum of the aggregates of all earlier tiles
+    // exclusive prefix of this tile = sum of the aggregates of all earlier tiles, two-level: whole groups of
+    // kScanGroup tiles, then the earlier tiles of this tile's own group (a flat loop over all earlier tiles
+    // was a 20-deep load chain and 25 MB of L2 reads at batch 8)
     unsigned long long pre = 0;
-    for (int t = tid; t < tile; t += kScanThreads) pre += a.agg[t];
+    const int g0 = tile / kScanGroup;
+    for (int g = tid; g < g0; g += kScanThreads) pre += a.agg_group[g];
+    if (tid < tile - g0 * kScanGroup) pre += a.agg[g0 * kScanGroup + tid];
 
     int c[kScanItems];
     if (base + kScanItems <= a.n_buckets) {
@@ -285,7 +292,7 @@ struct OrderArgs {
     // forward flavour outputs (nullptr for the backward plan)
     int32_t *ranks_feat;
     int32_t *ranks_bev;
-    int32_t dhw, hw;            // D*H*W and H*W: ranks_feat = (p / dhw) * hw + p % hw  (view_transformer.py:239-244)
+    FastDiv dhw, hw;            // D*H*W and H*W: ranks_feat = (p / dhw) * hw + p % hw  (view_transformer.py:239-244)
     // intervals longer than kLaneSortMax are queued here by the short pass and ordered, one warp each,
     // by the long pass — dense near-ego voxels are consecutive in voxel order, so without the queue a
     // few warps would inherit dozens of long intervals each (measured: 103 us -> tail-bound)
@@ -294,6 +301,12 @@ struct OrderArgs {
                                 // [1] = longer ones, queued from the END of long_list (long_cap - 1 downwards)
     int32_t long_cap;
 };
+
+// feature row of frustum point p: (p / dhw) * hw + p % hw
+__device__ __forceinline__ int feat_row_of(int p, const FastDiv &dhw, const FastDiv &hw) {
+    const uint32_t n = (uint32_t)p;
+    return (int)(fastdiv(n, dhw) * hw.d + (n - fastdiv(n, hw) * hw.d));
+}
 
 // 19-comparator optimal sorting network for 8 keys (ascending)
 __device__ __forceinline__ void sort8(int (&v)[8]) {
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
             if (j < len) {
                 if (len > 1) a.sorted[s + j] = v[j];
                 if (kForward) {
-                    if (a.ranks_feat) a.ranks_feat[s + j] = (v[j] / a.dhw) * a.hw + (v[j] % a.hw);
+                    if (a.ranks_feat) a.ranks_feat[s + j] = feat_row_of(v[j], a.dhw, a.hw);
                     a.ranks_bev[s + j] = bucket;
                 }
             }
@@ -376,7 +389,7 @@ __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
         if (kForward) {
             for (int j = lane; j < ll; j += 32) {
                 const int p = a.sorted[ls + j];
-                if (a.ranks_feat) a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                if (a.ranks_feat) a.ranks_feat[ls + j] = feat_row_of(p, a.dhw, a.hw);
                 a.ranks_bev[ls + j] = lb;
             }
         }
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
         if (kForward) {
             for (int j = threadIdx.x; j < ll; j += kSortThreads) {
                 const int p = a.sorted[ls + j];
-                if (a.ranks_feat) a.ranks_feat[ls + j] = (p / a.dhw) * a.hw + (p % a.hw);
+                if (a.ranks_feat) a.ranks_feat[ls + j] = feat_row_of(p, a.dhw, a.hw);
                 a.ranks_bev[ls + j] = lb;
             }
         }

@@ -128,7 +128,7 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
 // ----------------------------------------------------------------------------------------------
 // Backward plan buffer (the inverse interval ordering):
 //   [header(256) | starts[rows] | lengths[rows] | ids[rows] | bucket counters (generic build) |
-//    ent_p[cap] | ent_iv[cap] | pos[cap] | slot[cap]]
+//    ent_p[cap] | ent_iv[cap] | pos[cap] | slot[cap]]   (bucket counters = cnt | tile aggregates | group aggregates | queue counters)
 //   backward interval m (one image pixel) covers entries [starts[m], +lengths[m]); entry j names the
 //   point's depth index ent_p[j] and its forward interval ent_iv[j]; ids[m] is the feature row.
 //   Entries are in ascending forward position = the order bev_pool.py:47-49 produces.
@@ -141,9 +141,11 @@ struct BwdPlanView {
     int32_t *ent_p, *ent_iv, *pos, *slot;
     int64_t cap;
 };
+constexpr int kScanGroup = 16;   // scan tiles per aggregate group (two-level tile prefix)
 __host__ inline size_t bucket_zero_bytes(int64_t n_buckets) {
     const int64_t n_scan_tiles = (n_buckets + 2047) / 2048;
-    return (size_t)(align_up(n_buckets * 4, 256) + align_up(n_scan_tiles * 8, 256) + 256);
+    const int64_t n_groups = n_scan_tiles / kScanGroup + 1;
+    return (size_t)(align_up(n_buckets * 4, 256) + align_up(n_scan_tiles * 8, 256) + align_up(n_groups * 8, 256) + 256);
 }
 __host__ inline size_t bwd_plan_fixed_bytes(int64_t rows) {
     return 256 + 3 * (size_t)align_up(rows * 4, 256) + bucket_zero_bytes(rows);
@@ -214,6 +216,34 @@ inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Division of a 32-bit unsigned by a run-time invariant divisor (Granlund & Montgomery, "Division by invariant
+// integers using multiplication", fig. 4.1): q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(m, n); exact for
+// every n < 2^32 and 1 <= d < 2^31.  The order pass derives ranks_feat from the point index with two divisions per
+// point; a hardware-emulated 32-bit division costs ~20 instructions.
+// ----------------------------------------------------------------------------------------------
+struct FastDiv {
+    uint32_t m;
+    int32_t sh1, sh2;
+    uint32_t d;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    int l = 0;
+    while ((1ull << l) < d) ++l;                      // l = ceil(log2 d)
+    f.m = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 1 ? l - 1 : 0;
+    f.d = d;
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
+    const uint32_t t = __umulhi(f.m, n);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Small device helpers

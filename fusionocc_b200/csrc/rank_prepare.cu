@@ -434,6 +434,7 @@ int open_fwd_plan(void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64
 struct SortScratch {
     int32_t *cnt;
     unsigned long long *agg;     // per-scan-tile (points << 32 | non-empty buckets)
+    unsigned long long *agg_group;   // the same summed over groups of kScanGroup tiles (zero-initialised)
     int32_t *counter;            // long-interval queue length
     size_t zero_bytes;
 };
@@ -443,6 +444,7 @@ SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     char *p = (char *)base;
     s.cnt = (int32_t *)p;                       p += align_up(n_buckets * 4, 256);
     s.agg = (unsigned long long *)p;            p += align_up(n_scan_tiles * 8, 256);
+    s.agg_group = (unsigned long long *)p;      p += align_up((n_scan_tiles / kScanGroup + 1) * 8, 256);
     s.counter = (int32_t *)p;                   p += 256;
     s.zero_bytes = (size_t)(p - (char *)base);
     return s;
@@ -534,9 +536,9 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     sa.sub_iv = pv.sub_iv; sa.sub_pt = pv.sub_pt; sa.vox_per_sample = n_vox; sa.subs_per_sample = sps;
     sa.n_subs = (int)n_subs;
     sa.fwd_hdr = pv.hdr; sa.bwd_hdr = nullptr;
-    sa.agg = ss.agg;
+    sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((NV + kScanTile - 1) / kScanTile);
-    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, NV, ss.agg);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, NV, ss.agg, ss.agg_group);
     FO_LAUNCH_CHECK("tile_reduce_kernel");
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
@@ -548,7 +550,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     oa.sorted = ranks_depth; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev;
-    oa.dhw = D * H * W; oa.hw = H * W;
+    oa.dhw = make_fastdiv((uint32_t)(D * H * W)); oa.hw = make_fastdiv((uint32_t)(H * W));
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     oa.long_cap = (int32_t)P;
     const int64_t cap_iv = P < NV ? P : NV;
@@ -630,9 +632,9 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     sa.totals = counts_dev;
     sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = nullptr;
-    sa.agg = ss.agg;
+    sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((n_buckets + kScanTile - 1) / kScanTile);
-    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_buckets, ss.agg);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_buckets, ss.agg, ss.agg_group);
     FO_LAUNCH_CHECK("tile_reduce_kernel");
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
@@ -642,7 +644,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     oa.sorted = order; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = iv_bucket; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = nullptr; oa.ranks_bev = sorted_keys;
-    oa.dhw = 1; oa.hw = 1;
+    oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)n_points;
     const int64_t cap_iv = n_points < n_buckets ? n_points : n_buckets;
     order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
@@ -729,9 +731,9 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     sa.totals = bv.hdr->totals;
     sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = bv.hdr;
-    sa.agg = ss.agg;
+    sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((n_feat_rows + kScanTile - 1) / kScanTile);
-    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_feat_rows, ss.agg);
+    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, n_feat_rows, ss.agg, ss.agg_group);
     FO_LAUNCH_CHECK("tile_reduce_kernel");
     scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
     FO_LAUNCH_CHECK("scan_buckets_kernel");
@@ -741,7 +743,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     OrderArgs oa;
     oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
     oa.n_intervals = &bv.hdr->n_bwd_intervals;
-    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.dhw = 1; oa.hw = 1;
+    oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = bv.slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)bv.cap;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<bwd>");
