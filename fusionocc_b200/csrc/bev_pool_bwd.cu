@@ -162,7 +162,10 @@ constexpr int kPixChunk   = 32;     // points staged per pass: one per lane
 // All indices are 32-bit (the host checks rows * C < 2^31).
 template <int NACC, bool EXACT>
 __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
-    constexpr int U = NACC == 1 ? 16 : (NACC == 2 ? 8 : 4);   // gathered rows in flight per lane
+#ifndef FO_PIX_U
+#define FO_PIX_U 16
+#endif
+    constexpr int U = NACC == 1 ? FO_PIX_U : (NACC == 2 ? 8 : 4);   // gathered rows in flight per lane
     extern __shared__ __align__(16) float psm[];
     __shared__ __align__(16) int2 s_rec[kPixWarps][kPixChunk + 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -349,7 +352,10 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
     const int nacc = (C + 31) / 32;
     const bool idx32 = pa.n_rows_G * pa.g_rowstride < INT_MAX && pa.n_feat_rows * C < INT_MAX && pixels < INT_MAX;
     if (vec && idx32 && nacc <= 4 && smem <= 200 * 1024) {
-        const int blocks = grid_for(pixels, kPixWarps, 8);
+#ifndef FO_PIX_CTAS_PER_SM
+#define FO_PIX_CTAS_PER_SM 8
+#endif
+        const int blocks = grid_for(pixels, kPixWarps, FO_PIX_CTAS_PER_SM);
 #define FO_PIX(NA, EX)                                                                                          \
     do {                                                                                                        \
         if (smem > 48 * 1024)                                                                                   \
