@@ -558,3 +558,44 @@ def test_batch32_shard_matches_single_sample_runs():
         o.backward(g1)
         assert torch.equal(d.grad[0].view(torch.int32), depth.grad[b].view(torch.int32)), f'sample {b}: depth_grad'
         assert torch.equal(f.grad[0].view(torch.int32), feat.grad[b].view(torch.int32)), f'sample {b}: feat_grad'
+
+
+@pytest.mark.parametrize('grid,C,B', [((7, 5, 3), 5, 3), ((1, 1, 1), 32, 2), ((9, 2, 2), 36, 1), ((33, 1, 1), 8, 2)])
+def test_odd_grids_take_the_scalar_paths(grid, C, B):
+    """Voxel counts that are not a multiple of 4 / 32 (ragged last sub-tile, no 128-bit stores or loads), one-voxel
+    grids and channel counts that are not a multiple of 4: ranks exact, forward and both gradients bit-exact vs the
+    oracle, for the gradient of bev_pool_v2's output and for a channels-last gradient."""
+    from fusionocc_b200.bev_pool import bev_pool_v2_with_plan
+    from fusionocc_b200.view_transformer import rank_prepare
+    from oracle import kernels as ok, rank_oracle as ro
+    X, Y, Z = grid
+    N, D, H, W = 2, 7, 3, 5
+    g = torch.Generator().manual_seed(X * 100 + Y * 10 + Z)
+    lb = np.array([-1.0, -2.0, 0.5], np.float32)
+    itv = np.array([0.5, 0.25, 1.0], np.float32)
+    span = torch.tensor([X * 0.5, Y * 0.25, Z * 1.0])
+    coor = (torch.rand(B, N, D, H, W, 3, generator=g) * 1.4 - 0.2) * span + torch.from_numpy(lb)   # ~30 % outside
+    want = ro.voxel_pooling_prepare_v2(coor.numpy(), lb, itv, np.array([X, Y, Z], np.float32), 'int64')
+    rb, rd, rf, st, ln, counts, plan = rank_prepare(coor.to(dev()), lb.tolist(), itv.tolist(), (X, Y, Z))
+    nk, ni = (int(v) for v in counts[:2].tolist())
+    assert nk == len(want[0]) and ni == len(want[3])
+    for a, b, nm in zip((rb[:nk], rd[:nk], rf[:nk], st[:ni], ln[:ni]), want,
+                        ('ranks_bev', 'ranks_depth', 'ranks_feat', 'interval_starts', 'interval_lengths')):
+        assert np.array_equal(a.cpu().numpy(), b), nm
+    depth = torch.rand(B, N, D, H, W, generator=g)
+    feat = torch.randn(B, N, H, W, C, generator=g)
+    shape = (B, Z, Y, X, C)
+    w_out = ok.bev_pool_v2(depth.numpy(), feat.numpy(), want[1], want[2], want[0], shape, want[3], want[4])
+    og = torch.randn(B, C, Z, Y, X, generator=g)
+    w_dg, w_fg = ok.bev_pool_v2_backward(og.numpy(), depth.numpy(), feat.numpy(), want[1], want[2], want[0])
+    for channels_last in (False, True):
+        d = depth.to(dev()).requires_grad_()
+        f = feat.to(dev()).requires_grad_()
+        out = bev_pool_v2_with_plan(d, f, rd, rf, rb, shape, st, ln, plan)
+        assert_bit_equal(out, w_out, f'forward {grid}')
+        gr = og.to(dev())
+        if channels_last:
+            gr = gr.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+        out.backward(gr)
+        assert_bit_equal(d.grad, w_dg, f'depth_grad {grid} cl={channels_last}')
+        assert_bit_equal(f.grad, w_fg, f'feat_grad {grid} cl={channels_last}')
