@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
     const unsigned my_col = rows_s + 4u * lane;                              // column `lane` of row 0
     int2 *rec = s_rec[warp];
     const int n = a.n_bwd_dev ? min(max(*a.n_bwd_dev, 0), (int)a.n_bwd) : (int)a.n_bwd;
-    const int warp0 = blockIdx.x * kPixWarps + warp;
-    const int nwarps = gridDim.x * kPixWarps;
+    const int cta_warps = blockDim.x >> 5;                                   // <= kPixWarps
+    const int warp0 = blockIdx.x * cta_warps + warp;
+    const int nwarps = gridDim.x * cta_warps;
     const int n_depth = (int)a.n_depth, n_rows_G = (int)a.n_rows_G, n_iv = (int)a.n_iv;
 
     for (int m = warp0; m < n; m += nwarps) {
@@ -348,20 +349,25 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
     const int64_t pixels = pa.n_bwd;
     if (pixels <= 0) return FO_OK;
     const int C = pa.C;
-    const size_t smem = (size_t)kPixWarps * (kPixChunk * (C + 4) + C) * sizeof(float);
+#ifndef FO_PIX_WARPS_BIGC
+#define FO_PIX_WARPS_BIGC 8
+#endif
     const int nacc = (C + 31) / 32;
+    // the per-warp tile grows with C: smaller CTAs keep more warps resident for wide channel counts
+    const int cta_warps = nacc >= 3 ? FO_PIX_WARPS_BIGC : kPixWarps;
+    const size_t smem = (size_t)cta_warps * (kPixChunk * (C + 4) + C) * sizeof(float);
     const bool idx32 = pa.n_rows_G * pa.g_rowstride < INT_MAX && pa.n_feat_rows * C < INT_MAX && pixels < INT_MAX;
     if (vec && idx32 && nacc <= 4 && smem <= 200 * 1024) {
 #ifndef FO_PIX_CTAS_PER_SM
 #define FO_PIX_CTAS_PER_SM 8
 #endif
-        const int blocks = grid_for(pixels, kPixWarps, FO_PIX_CTAS_PER_SM);
+        const int blocks = grid_for(pixels, cta_warps, FO_PIX_CTAS_PER_SM * kPixWarps / cta_warps);
 #define FO_PIX(NA, EX)                                                                                          \
     do {                                                                                                        \
         if (smem > 48 * 1024)                                                                                   \
             FO_CUDA(cudaFuncSetAttribute(bwd_pixel_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                           \
-        bwd_pixel_kernel<NA, EX><<<blocks, kPixThreads, smem, stream>>>(pa);                                    \
+        bwd_pixel_kernel<NA, EX><<<blocks, 32 * cta_warps, smem, stream>>>(pa);                                 \
     } while (0)
         if (C % 32 == 0) {
             switch (nacc) {
