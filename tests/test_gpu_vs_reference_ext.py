@@ -17,7 +17,7 @@ def _ref():
     return ref_ext
 
 
-@pytest.mark.parametrize('name,B', [('base', 1), ('base', 8), ('stress', 1)])
+@pytest.mark.parametrize('name,B', [('base', 1), ('base', 8), ('native', 2), ('stress', 1), ('stress', 2)])
 def test_forward_and_backward_bit_identical_to_reference_extension(name, B):
     ref = _ref()
     from fusionocc_b200 import bev_pool_v2
