@@ -22,8 +22,14 @@
 
 namespace fo {
 
-constexpr int kScanThreads = 128;
-constexpr int kScanItems   = 16;                          // buckets per thread (4 x int4)
+#ifndef FO_SCAN_THREADS
+#define FO_SCAN_THREADS 128
+#endif
+#ifndef FO_SCAN_ITEMS
+#define FO_SCAN_ITEMS 16
+#endif
+constexpr int kScanThreads = FO_SCAN_THREADS;
+constexpr int kScanItems   = FO_SCAN_ITEMS;               // buckets per thread (multiple of 4: int4 accesses)
 constexpr int kScanTile    = kScanThreads * kScanItems;   // 2048 buckets per CTA
 
 // Per-scan-tile aggregates (points << 32 | non-empty buckets) come from a separate reduce pass over the

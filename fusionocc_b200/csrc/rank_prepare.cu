@@ -449,7 +449,7 @@ SortScratch sort_scratch_view(void *base, int64_t n_buckets) {
     s.zero_bytes = (size_t)(p - (char *)base);
     return s;
 }
-static_assert(kScanTile == 2048, "bucket_zero_bytes() in common.cuh assumes 2048-bucket scan tiles");
+static_assert(kScanTile >= 2048 && kScanItems % 4 == 0, "bucket_zero_bytes() in common.cuh sizes the aggregates for 2048-bucket scan tiles");
 }  // namespace
 
 // exported for the other translation units

@@ -599,3 +599,17 @@ def test_odd_grids_take_the_scalar_paths(grid, C, B):
         out.backward(gr)
         assert_bit_equal(d.grad, w_dg, f'depth_grad {grid} cl={channels_last}')
         assert_bit_equal(f.grad, w_fg, f'feat_grad {grid} cl={channels_last}')
+
+
+def test_empty_rank_arrays_give_zero_output_and_zero_gradients():
+    """Op-level empty case (the reference would launch a 0-block grid): zero points / intervals
+    must produce an all-zero voxel tensor and all-zero gradients, through the dense path and its plans."""
+    from fusionocc_b200 import bev_pool_v2
+    B, N, D, H, W, C, Z, Y, X = 2, 2, 3, 2, 3, 8, 2, 4, 8
+    e = torch.empty(0, dtype=torch.int32, device=dev())
+    d = torch.rand(B, N, D, H, W, device=dev()).requires_grad_()
+    f = torch.randn(B, N, H, W, C, device=dev()).requires_grad_()
+    out = bev_pool_v2(d, f, e, e, e, (B, Z, Y, X, C), e, e)
+    assert out.shape == (B, C, Z, Y, X) and bool((out.view(torch.int32) == 0).all())
+    out.backward(torch.ones_like(out))
+    assert bool((d.grad == 0).all()) and bool((f.grad == 0).all())
