@@ -43,14 +43,17 @@ def test_forward_and_backward_vs_torch(dtype, BN, D, C, H, W, extra):
         assert bool((xb.grad[:, D + C:] == 0).all())
 
 
-def test_module_fuse_lift_matches_unfused_forward():
-    """LSSViewTransformer(fuse_lift=True).forward == the reference-order forward within 1e-5, grads included."""
+@pytest.mark.parametrize('fuse_geometry', [False, True])
+def test_module_fuse_lift_matches_unfused_forward(fuse_geometry):
+    """LSSViewTransformer(fuse_lift=True[, fuse_geometry=True]).forward == the reference-order forward within
+    tolerance, gradients included."""
     sh = SHAPES['small']
     B = 2
     torch.manual_seed(0)
     kw = dict(in_channels=16, out_channels=sh.channels, collapse_z=False)
     vt = LSSViewTransformer(sh.grid_cfg(), sh.input_size, sh.downsample, **kw).to(DEV)
-    vt_f = LSSViewTransformer(sh.grid_cfg(), sh.input_size, sh.downsample, fuse_lift=True, **kw).to(DEV)
+    vt_f = LSSViewTransformer(sh.grid_cfg(), sh.input_size, sh.downsample, fuse_lift=True,
+                              fuse_geometry=fuse_geometry, **kw).to(DEV)
     vt_f.load_state_dict(vt.state_dict())
     cal = [c.to(DEV) for c in make_calibration(sh, B)]
     H, W = sh.feat_hw
