@@ -73,7 +73,10 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 #define FO_FWD_HEAVY_PTS 256
 #endif
 constexpr int kHeavyPts   = FO_FWD_HEAVY_PTS;   // short launches: sub-tiles with more points go to the multi-warp kernel
-constexpr int kHeavyWarps = 8;
+#ifndef FO_FWD_HEAVY_WARPS
+#define FO_FWD_HEAVY_WARPS 16
+#endif
+constexpr int kHeavyWarps = FO_FWD_HEAVY_WARPS;   // measured 8 / 16 / 32 warps x 1-4 CTAs per SM: 16 x 2 is the best compromise
 #ifndef FO_FWD_HEAVY_MAX_MB
 #define FO_FWD_HEAVY_MAX_MB 256
 #endif
@@ -193,7 +196,7 @@ __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, con
 //
 // Sub-tiles with more than kHeavyPts points are not reduced here: their serial FMA chain (3 394 points at
 // 512x1408, 844 at the headline shape) is the critical path of a small launch (batch 1), so they are queued
-// for fwd_heavy_kernel, which splits a sub-tile's VOXELS over eight warps.
+// for fwd_heavy_kernel, which splits a sub-tile's VOXELS over sixteen warps.
 template <int NACC, bool EXACT, int LAYOUT>
 __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
     extern __shared__ __align__(16) float smem[];        // stage [C][32]
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
 }
 
 // Dense sub-tiles (> kHeavyPts points): one CTA of kHeavyWarps warps per queued sub-tile.  The sub-tile's
-// intervals (<= 32, one per occupied voxel) are split into kHeavyWarps contiguous groups of about equal point
+// intervals (<= 32, one per occupied voxel) are split into kHeavyWarps (16) contiguous groups of about equal point
 // count; every warp reduces its group into the CTA's shared stage (distinct voxel columns), then the block is
 // written out by all warps.  Only the (B,C,Z,Y,X) layout with V % 4 == 0 queues sub-tiles.  The last CTA to
 // finish re-arms the queue for the next launch: a plan serves one forward launch at a time.
