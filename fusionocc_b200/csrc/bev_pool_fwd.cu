@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
 // count; every warp reduces its group into the CTA's shared stage (distinct voxel columns), then the block is
 // written out by all warps.  Only the (B,C,Z,Y,X) layout with V % 4 == 0 queues sub-tiles.  The last CTA to
 // finish re-arms the queue for the next launch: a plan serves one forward launch at a time.
+#ifndef FO_FWD_HEAVY_MINCTAS
+#define FO_FWD_HEAVY_MINCTAS 1
+#endif
 template <int NACC, bool EXACT>
-__global__ void __launch_bounds__(32 * kHeavyWarps) fwd_heavy_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(32 * kHeavyWarps, FO_FWD_HEAVY_MINCTAS) fwd_heavy_kernel(FwdArgs a) {
     extern __shared__ __align__(16) float smem[];        // stage [C][32], shared by the CTA
     __shared__ __align__(16) int s_rx[kHeavyWarps][32 + 8];
     __shared__ __align__(16) float s_rd[kHeavyWarps][32 + 8];
@@ -312,7 +315,13 @@ __global__ void __launch_bounds__(32 * kHeavyWarps) fwd_heavy_kernel(FwdArgs a) 
     const int sps = a.sps;
     const int64_t V = a.V;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    __shared__ int s_next;
+    for (;;) {
+        // queue entries are handed out dynamically: their cost varies by an order of magnitude
+        if (threadIdx.x == 0) s_next = atomicAdd(a.heavy_ctl + 2, 1);
+        __syncthreads();
+        const int h = s_next;
+        if (h >= n_heavy) break;
         const int u = a.heavy_list[h];
         const int b = u / sps, su = u - b * sps;
         const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
@@ -351,6 +360,7 @@ __global__ void __launch_bounds__(32 * kHeavyWarps) fwd_heavy_kernel(FwdArgs a) 
         if (atomicAdd(a.heavy_ctl + 1, 1) == (int)gridDim.x - 1) {
             a.heavy_ctl[0] = 0;
             a.heavy_ctl[1] = 0;
+            a.heavy_ctl[2] = 0;
             __threadfence();
         }
     }

@@ -50,8 +50,9 @@ struct __align__(16) FwdPlanHeader {
     int32_t subs_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
     int32_t structured;      // 1: pt2vox / vox2iv are valid (plan produced by fo_rank_prepare)
-    int32_t fwd_heavy[2];    // forward: queue length of dense sub-tiles, heavy-kernel CTAs done (0 between launches)
-    int32_t reserved[9];
+    int32_t fwd_heavy[3];    // forward: queue length of dense sub-tiles, heavy-kernel CTAs done, next queue entry
+                             // to hand out (all 0 between launches)
+    int32_t reserved[8];
 };
 static_assert(sizeof(FwdPlanHeader) == 64, "header is one 64-byte block");
 

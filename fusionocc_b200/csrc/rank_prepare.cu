@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a, CalibArg
         a.hdr->n_subs = a.n_subs;
         a.hdr->subs_per_sample = a.subs_per_sample;
         a.hdr->structured = 1;
-        a.hdr->fwd_heavy[0] = a.hdr->fwd_heavy[1] = 0;
+        a.hdr->fwd_heavy[0] = a.hdr->fwd_heavy[1] = a.hdr->fwd_heavy[2] = 0;
     }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_quads = a.n_points >> 2;
@@ -177,7 +177,7 @@ __global__ void init_fwd_header_kernel(FwdPlanHeader *hdr, int n_subs, int sps, 
         hdr->subs_per_sample = sps;
         hdr->n_intervals = n_intervals;
         hdr->structured = 0;
-        hdr->fwd_heavy[0] = hdr->fwd_heavy[1] = 0;
+        hdr->fwd_heavy[0] = hdr->fwd_heavy[1] = hdr->fwd_heavy[2] = 0;
     }
 }
 
