@@ -91,11 +91,10 @@ constexpr int64_t kHeavyMaxOutBytes = (int64_t)FO_FWD_HEAVY_MAX_MB << 20;   // l
 //   * record words / depth values are broadcast through shared memory (LDS.128, no shuffles), feature rows
 //     are fetched in groups of U with the NEXT group already in flight (2*U rows in flight per lane), and the
 //     next 32 records are fetched while a batch is processed.
-template <int NACC, bool EXACT>
+template <int NACC, bool EXACT, int U = (NACC <= 2 ? FO_FWD_U : 4)>   // U = feature rows per group
 __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, const int lane, const int p_lo,
                                               const int p_hi, const int bV, int *rx, float *rdv,
                                               const unsigned lane_row, const unsigned lane_rot) {
-    constexpr int U = NACC <= 2 ? FO_FWD_U : 4;          // feature rows per group
     int mx = 0, mr = -1;
     auto load_idx = [&](int i0) {
         mx = 0; mr = -1;
@@ -152,7 +151,7 @@ __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, con
         const int n = min(32, p_hi - i0);
         __syncwarp();
         rx[lane] = mx;
-        if (lane < 8) { rx[32 + lane] = 0; rdv[32 + lane] = 0.f; }
+        if (lane < U) { rx[32 + lane] = 0; rdv[32 + lane] = 0.f; }
         __syncwarp();
         const int nfull = n & ~(U - 1);
         float fa[U][NACC], fb[U][NACC];
@@ -306,9 +305,14 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
 #endif
 template <int NACC, bool EXACT>
 __global__ void __launch_bounds__(32 * kHeavyWarps, FO_FWD_HEAVY_MINCTAS) fwd_heavy_kernel(FwdArgs a) {
+#ifndef FO_FWD_HEAVY_U
+#define FO_FWD_HEAVY_U 16
+#endif
+    // one long interval is one serial FMA chain: only more feature rows in flight shorten it
+    constexpr int kHeavyU = FO_FWD_HEAVY_U ? (NACC == 1 ? FO_FWD_HEAVY_U : FO_FWD_HEAVY_U / 2) : (NACC <= 2 ? FO_FWD_U : 4);
     extern __shared__ __align__(16) float smem[];        // stage [C][32], shared by the CTA
-    __shared__ __align__(16) int s_rx[kHeavyWarps][32 + 8];
-    __shared__ __align__(16) float s_rd[kHeavyWarps][32 + 8];
+    __shared__ __align__(16) int s_rx[kHeavyWarps][32 + 16];
+    __shared__ __align__(16) float s_rd[kHeavyWarps][32 + 16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = EXACT ? 32 * NACC : a.C;
     const int n_heavy = *a.heavy_ctl;
@@ -342,8 +346,8 @@ __global__ void __launch_bounds__(32 * kHeavyWarps, FO_FWD_HEAVY_MINCTAS) fwd_he
         }
         __syncthreads();                                  // the stage is zeroed
         if (mine)
-            reduce_points<NACC, EXACT>(a, C, lane, p_lo, p_hi, b * (int)V, s_rx[warp], s_rd[warp],
-                                       sbase + ((unsigned)lane << 7), ((unsigned)lane & 7u) << 4);
+            reduce_points<NACC, EXACT, kHeavyU>(a, C, lane, p_lo, p_hi, b * (int)V, s_rx[warp], s_rd[warp],
+                                                sbase + ((unsigned)lane << 7), ((unsigned)lane & 7u) << 4);
         __syncthreads();
         // write-out: lane -> (row of a quad, 16-byte chunk); quads of rows are dealt to the warps
         const int riq = lane >> 3, chunk = lane & 7;
