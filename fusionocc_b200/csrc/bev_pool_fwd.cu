@@ -12,9 +12,11 @@
 //   * lanes = channels: each point's 128-byte feature row is one coalesced load; the accumulator is the
 //     reference's exact FFMA chain (psum = fmaf(feat, depth, psum) from +0.0f, in point order); when the
 //     voxel id changes the finished accumulator is flushed to the warp's shared-memory stage;
-//   * the stage is the output block's own layout, [C][32] with an XOR-swizzled 16-byte chunk index, so
+//   * the stage is the output block's own layout, [C][32] with rows rotated by (c & 7) 16-byte chunks, so
 //     the write-out is LDS.128 -> streaming STG.128, four full 128-byte lines per instruction;
-//   * no __syncthreads anywhere: 48 independent warps per SM hide the 3-round-trip dependency chain.
+//   * single-warp CTAs, no __syncthreads in the main kernel: up to 32 independent warps per SM walk the
+//     3-round-trip dependency chain of their sub-tiles; the few very dense sub-tiles of a short launch are
+//     queued for fwd_heavy_kernel, which splits one sub-tile's voxels over sixteen warps.
 #include "common.cuh"
 
 namespace fo {
