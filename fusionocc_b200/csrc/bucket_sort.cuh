@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) 
 
 // ----------------------------------------------------------------------------------------------
 // In-segment ordering.  One lane per interval for the short ones (len <= 8: sorting network in
-// registers); longer intervals are handled one at a time by a whole warp in registers (bitonic for
-// len <= 32, rank-by-counting for len <= 128) or by a whole CTA in shared memory (len <= kSortSmemCta);
+// registers); longer intervals are handled one at a time by a whole warp in registers (bitonic networks over
+// 1 / 2 / 4 registers per lane for len <= 32 / 64 / 128) or by a whole CTA in shared memory (len <= kSortSmemCta);
 // beyond that (degenerate geometry) a single warp runs the network in global memory.
 // ----------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 128;
@@ -231,39 +231,24 @@ __device__ inline void warp_sort_segment(int32_t *seg, int len, int * /*unused*/
         if (lane < len) seg[lane] = v;
         return;
     }
-    if (len <= 128) {
-        // rank by counting in registers: all keys are distinct, so the rank of a key is the number of
-        // smaller keys (4 keys per lane, 128 broadcasts)
-        int v[4], rank[4];
+    if (len <= 64) {                                   // bitonic network over 2 registers per lane: 21 steps x 2
+        int v[2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { v[r] = (lane + 32 * r < len) ? seg[lane + 32 * r] : INT_MAX; rank[r] = 0; }
-        if (len <= 64) {
+        for (int r = 0; r < 2; ++r) v[r] = (lane + 32 * r < len) ? seg[lane + 32 * r] : INT_MAX;
+        bitonic_sort_regs<2>(v, lane);
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-#pragma unroll 8
-                for (int l = 0; l < 32; ++l) {
-                    const int other = __shfl_sync(0xffffffffu, v[rr], l);
-                    rank[0] += (other < v[0]) ? 1 : 0;
-                    rank[1] += (other < v[1]) ? 1 : 0;
-                }
-            }
-        } else {
+        for (int r = 0; r < 2; ++r)
+            if (lane + 32 * r < len) seg[lane + 32 * r] = v[r];
+        return;
+    }
+    if (len <= 128) {                                  // ... over 4 registers per lane: 28 steps x 4 (rank-by-counting
+        int v[4];                                      // needed 128 broadcasts x 4 compares)
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                if (32 * rr < len) {
-#pragma unroll 8
-                    for (int l = 0; l < 32; ++l) {
-                        const int other = __shfl_sync(0xffffffffu, v[rr], l);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) rank[r] += (other < v[r]) ? 1 : 0;
-                    }
-                }
-            }
-        }
-        __syncwarp();
+        for (int r = 0; r < 4; ++r) v[r] = (lane + 32 * r < len) ? seg[lane + 32 * r] : INT_MAX;
+        bitonic_sort_regs<4>(v, lane);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            if (v[r] != INT_MAX) seg[rank[r]] = v[r];
+            if (lane + 32 * r < len) seg[lane + 32 * r] = v[r];
         return;
     }
     int n2 = 256;

@@ -250,6 +250,36 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 // Small device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+template <int RS>   // ascending bitonic sort of 32*RS keys, element e = 32 r + lane
+__device__ __forceinline__ void bitonic_sort_regs(int (&key)[RS], const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * RS; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {                               // partner in another register of the same lane
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const int pr = r ^ (j >> 5);
+                    if (pr > r) {
+                        const bool up = (((32 * r) & k) == 0);
+                        const int lo = min(key[r], key[pr]), hi = max(key[r], key[pr]);
+                        key[r] = up ? lo : hi;
+                        key[pr] = up ? hi : lo;
+                    }
+                }
+            } else {                                     // partner in lane ^ j, same register
+#pragma unroll
+                for (int r = 0; r < RS; ++r) {
+                    const int other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                    const bool up = ((((32 * r) | lane) & k) == 0);
+                    const bool lower = (lane & j) == 0;
+                    key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // Per-warp shared-memory stage of one sub-tile: channel-major [C][kSub] floats = the layout of the

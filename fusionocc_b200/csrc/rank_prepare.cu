@@ -293,36 +293,6 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
 // and D <= 128.  Only ~57 % of a pixel's depth bins land inside the grid, so the valid keys are first COMPACTED
 // (ballot + popc through a per-warp shared-memory row) and the network is sized to the live count: 32 / 64 / 128
 // elements = 15 / 21x2 / 28x4 compare-exchange steps (the kernel is issue-bound: 34 -> 2x us at the headline shape).
-template <int RS>   // ascending bitonic sort of 32*RS keys, element e = 32 r + lane
-__device__ __forceinline__ void bitonic_sort_regs(int (&key)[RS], const int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32 * RS; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {                               // partner in another register of the same lane
-#pragma unroll
-                for (int r = 0; r < RS; ++r) {
-                    const int pr = r ^ (j >> 5);
-                    if (pr > r) {
-                        const bool up = (((32 * r) & k) == 0);
-                        const int lo = min(key[r], key[pr]), hi = max(key[r], key[pr]);
-                        key[r] = up ? lo : hi;
-                        key[pr] = up ? hi : lo;
-                    }
-                }
-            } else {                                     // partner in lane ^ j, same register
-#pragma unroll
-                for (int r = 0; r < RS; ++r) {
-                    const int other = __shfl_xor_sync(0xffffffffu, key[r], j);
-                    const bool up = ((((32 * r) | lane) & k) == 0);
-                    const bool lower = (lane & j) == 0;
-                    key[r] = (lower == up) ? min(key[r], other) : max(key[r], other);
-                }
-            }
-        }
-    }
-}
-
 template <int RS>
 __device__ __forceinline__ void plan_sort_emit(const int *cmp, const int n, const int lane, const int ebase,
                                                const int pbase, const int HW, const int32_t *__restrict__ vox2iv,
