@@ -15,8 +15,8 @@
 //   * the stage is the output block's own layout, [C][32] with rows rotated by (c & 7) 16-byte chunks, so
 //     the write-out is LDS.128 -> streaming STG.128, four full 128-byte lines per instruction;
 //   * single-warp CTAs, no __syncthreads in the main kernel: up to 32 independent warps per SM walk the
-//     3-round-trip dependency chain of their sub-tiles; the few very dense sub-tiles of a short launch are
-//     queued for fwd_heavy_kernel, which splits one sub-tile's voxels over sixteen warps.
+//     3-round-trip dependency chain of their sub-tiles; the few very dense sub-tiles (listed by the plan) are
+//     split over eight "front" CTAs each, which start first.
 #include "common.cuh"
 
 namespace fo {
@@ -36,10 +36,12 @@ struct FwdArgs {
     const int32_t *sub_pt;
     int64_t out_bstride;            // (B,C,Z,Y,X) output: elements between samples (C_total * V; C * V when not a slice)
     int64_t out_rowstride;          // (B,Z,Y,X,C) output: elements between voxels   (C_total; C when not a slice)
-    const int32_t *sub_iv;          // heavy path: first interval of every sub-tile
-    int32_t *heavy_list;            // queue of dense sub-tiles (nullptr: everything is reduced by fwd_dense_kernel)
-    int32_t heavy_pts;              // sub-tiles with more points are queued
-    int32_t *heavy_ctl;             // [0] queue length, [1] CTAs of fwd_heavy_kernel done (both 0 between launches)
+    // dense sub-tiles (more than kHeavyPts points): listed by the plan, reduced by the "front" CTAs of the grid
+    const int32_t *sub_iv;          // first interval of every sub-tile
+    const int32_t *iv_vox;          // voxel id of every interval
+    const int32_t *heavy_list;      // sub-tile ids
+    const int32_t *n_heavy;         // device count
+    int32_t front_y;                // grid rows (blockIdx.y) reserved for front CTAs; 0: everything inline
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
 };
@@ -71,18 +73,8 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 #ifndef FO_FWD_MIN_CTAS
 #define FO_FWD_MIN_CTAS 32          // <= 64 registers: 32 single-warp CTAs per SM (the hardware's CTA limit)
 #endif
-#ifndef FO_FWD_HEAVY_PTS
-#define FO_FWD_HEAVY_PTS 256
-#endif
-constexpr int kHeavyPts   = FO_FWD_HEAVY_PTS;   // short launches: sub-tiles with more points go to the multi-warp kernel
-#ifndef FO_FWD_HEAVY_WARPS
-#define FO_FWD_HEAVY_WARPS 16
-#endif
-constexpr int kHeavyWarps = FO_FWD_HEAVY_WARPS;   // measured 8 / 16 / 32 warps x 1-4 CTAs per SM: 16 x 2 is the best compromise
-#ifndef FO_FWD_HEAVY_MAX_MB
-#define FO_FWD_HEAVY_MAX_MB 256
-#endif
-constexpr int64_t kHeavyMaxOutBytes = (int64_t)FO_FWD_HEAVY_MAX_MB << 20;   // larger launches keep dense sub-tiles inline
+constexpr int kFrontGroups = 8;     // a dense sub-tile is split into this many front CTAs
+constexpr int kFrontSlots  = 4096;  // front CTAs per launch (they loop over the list)
 
 // The reduction of one warp: points [p_lo, p_hi) of the sorted rank arrays, all inside one sub-tile, are
 // accumulated voxel by voxel — psum = fmaf(feat, depth, psum) from +0.0f in point order, the reference's
@@ -195,9 +187,12 @@ __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, con
 // >= 256-byte-per-plane write-out: 166/175/193 us; 21-25 instead of 32 resident CTAs per SM: 159-172 us;
 // write-back / .cg / .wt instead of streaming stores: 169 us; this version: 149-152 us.
 //
-// Sub-tiles with more than kHeavyPts points are not reduced here: their serial FMA chain (3 394 points at
-// 512x1408, 844 at the headline shape) is the critical path of a small launch (batch 1), so they are queued
-// for fwd_heavy_kernel, which splits a sub-tile's VOXELS over sixteen warps.
+// Dense sub-tiles (more than kHeavyPts points; the plan lists them): their serial FMA chain (3 394 points at
+// 512x1408, 844 at the headline shape) would be the critical path of a short launch and a tail of a long one.
+// The first rows of the grid are FRONT CTAs: each takes one of kFrontGroups contiguous interval groups (about equal
+// point counts) of a listed sub-tile, reduces it into its own stage and writes exactly the voxel columns from its
+// first interval's voxel up to the next group's — so the groups tile the sub-tile and every element is still
+// written once.  They start first and overlap with the bulk of the grid; regular CTAs skip listed sub-tiles.
 template <int NACC, bool EXACT, int LAYOUT>
 __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
     extern __shared__ __align__(16) float smem[];        // stage [C][32]
@@ -209,13 +204,54 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
     // grid = (B, subs_per_sample): x-fastest block order interleaves the samples, so the dense near-ego
     // regions of all samples are reached at the same relative time
     const int sps = a.sps;
+    const int64_t V = a.V;
+    if ((int)blockIdx.y < a.front_y) {                    // ---- front CTA: one group of a dense sub-tile ----
+        if (a.check_flags && (__ldg(&a.hdr->flags) & kFlagUnsorted)) return;
+        const int n_tasks = __ldg(a.n_heavy) * kFrontGroups;
+        const unsigned sb = (unsigned)__cvta_generic_to_shared(smem);
+        for (int e = blockIdx.y * gridDim.x + blockIdx.x; e < n_tasks; e += a.front_y * gridDim.x) {
+            const int u = __ldg(a.heavy_list + e / kFrontGroups), g = e % kFrontGroups;
+            const int hb = u / sps, hsu = u - hb * sps;
+            const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
+            const int ia = __ldg(a.sub_iv + u), ni = min(__ldg(a.sub_iv + u + 1) - ia, kSub);
+            const int hv0 = hsu << kSubShift, hbV = hb * (int)V;
+            const int nv = min(kSub, (int)V - hv0);
+            int s_l = pb, v_l = nv;                       // first point / voxel slot of this lane's interval
+            if (lane < ni) { s_l = __ldg(a.starts + ia + lane); v_l = __ldg(a.iv_vox + ia + lane) - hbV - hv0; }
+            const int share = (int)(((long long)(s_l - pa) * kFrontGroups) / (pb - pa));
+            // cut(g) = first interval whose share is >= g: group g owns intervals [cut(g), cut(g+1))
+            const unsigned m0 = __ballot_sync(0xffffffffu, lane < ni && share >= g);
+            const unsigned m1 = (g + 1 < kFrontGroups) ? __ballot_sync(0xffffffffu, lane < ni && share >= g + 1) : 0u;
+            const int c0 = m0 ? __ffs(m0) - 1 : ni, c1 = m1 ? __ffs(m1) - 1 : ni;
+            const int vs0 = __shfl_sync(0xffffffffu, v_l, min(c0, 31)), vs1 = __shfl_sync(0xffffffffu, v_l, min(c1, 31));
+            const int ps0 = __shfl_sync(0xffffffffu, s_l, min(c0, 31)), ps1 = __shfl_sync(0xffffffffu, s_l, min(c1, 31));
+            const int vstart = (g == 0) ? 0 : (c0 < ni ? vs0 : nv), vend = (c1 < ni) ? vs1 : nv;
+            const int p_lo = (c0 < ni) ? ps0 : pb, p_hi = (c1 < ni) ? ps1 : pb;
+            if (vstart >= vend) continue;                 // (warp-uniform) an empty group owns no voxels
+            if (EXACT) {
+#pragma unroll
+                for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sb + 16u * lane + 512u * i);
+            } else {
+                for (int i = lane; i < C * (kSub / 4); i += 32) sts_zero4(sb + 16u * i);
+            }
+            if (p_lo < p_hi)
+                reduce_points<NACC, EXACT>(a, C, lane, p_lo, p_hi, hbV, s_rx, s_rd, sb + ((unsigned)lane << 7),
+                                           ((unsigned)lane & 7u) << 4);
+            __syncwarp();
+            if (lane >= vstart && lane < vend) {          // one voxel column per lane, one channel plane per store
+                float *dst = a.out + (int64_t)hb * a.out_bstride + hv0 + lane;
+                for (int c = 0; c < C; ++c) __stcs(dst + (int64_t)c * V, smem[stage_index(c, lane)]);
+            }
+            __syncwarp();                                 // the stage is reused by the next task
+        }
+        return;
+    }
     const int b = blockIdx.x;
-    const int su = blockIdx.y;
+    const int su = blockIdx.y - a.front_y;
     // one round trip: the plan's flag word and the point range are independent loads
     const int flags = a.check_flags ? __ldg(&a.hdr->flags) : 0;
     const int pa = __ldg(a.sub_pt + b * sps + su), pb = __ldg(a.sub_pt + b * sps + su + 1);
     if (flags & kFlagUnsorted) return;                   // the order-agnostic path runs instead
-    const int64_t V = a.V;
     const int bV = b * (int)V;                           // global voxel id of the sample's first voxel (< 2^31)
     const int v0 = su << kSubShift;
     const int nv = min(kSub, (int)V - v0);
@@ -238,10 +274,7 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
         }
         return;
     }
-    if (a.heavy_list != nullptr && pb - pa > a.heavy_pts) {   // queued for the multi-warp kernel
-        if (lane == 0) a.heavy_list[atomicAdd(a.heavy_ctl, 1)] = b * sps + su;
-        return;
-    }
+    if (a.front_y > 0 && pb - pa > kHeavyPts) return;    // a dense sub-tile: the front CTAs own it
     if (EXACT) {
 #pragma unroll
         for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
@@ -293,81 +326,6 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
         for (int e = lane; e < nv * C; e += 32) {
             const int v = e / C, c = e - v * C;
             __stcs(dst + (int64_t)v * a.out_rowstride + c, stage[stage_index(c, v)]);
-        }
-    }
-}
-
-// Dense sub-tiles (> kHeavyPts points): one CTA of kHeavyWarps warps per queued sub-tile.  The sub-tile's
-// intervals (<= 32, one per occupied voxel) are split into kHeavyWarps (16) contiguous groups of about equal point
-// count; every warp reduces its group into the CTA's shared stage (distinct voxel columns), then the block is
-// written out by all warps.  Only the (B,C,Z,Y,X) layout with V % 4 == 0 queues sub-tiles.  The last CTA to
-// finish re-arms the queue for the next launch: a plan serves one forward launch at a time.
-#ifndef FO_FWD_HEAVY_MINCTAS
-#define FO_FWD_HEAVY_MINCTAS 1
-#endif
-template <int NACC, bool EXACT>
-__global__ void __launch_bounds__(32 * kHeavyWarps, FO_FWD_HEAVY_MINCTAS) fwd_heavy_kernel(FwdArgs a) {
-#ifndef FO_FWD_HEAVY_U
-#define FO_FWD_HEAVY_U 16
-#endif
-    // one long interval is one serial FMA chain: only more feature rows in flight shorten it
-    constexpr int kHeavyU = FO_FWD_HEAVY_U ? (NACC == 1 ? FO_FWD_HEAVY_U : FO_FWD_HEAVY_U / 2) : (NACC <= 2 ? FO_FWD_U : 4);
-    extern __shared__ __align__(16) float smem[];        // stage [C][32], shared by the CTA
-    __shared__ __align__(16) int s_rx[kHeavyWarps][32 + 16];
-    __shared__ __align__(16) float s_rd[kHeavyWarps][32 + 16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = EXACT ? 32 * NACC : a.C;
-    const int n_heavy = *a.heavy_ctl;
-    const int sps = a.sps;
-    const int64_t V = a.V;
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-    __shared__ int s_next;
-    for (;;) {
-        // queue entries are handed out dynamically: their cost varies by an order of magnitude
-        if (threadIdx.x == 0) s_next = atomicAdd(a.heavy_ctl + 2, 1);
-        __syncthreads();
-        const int h = s_next;
-        if (h >= n_heavy) break;
-        const int u = a.heavy_list[h];
-        const int b = u / sps, su = u - b * sps;
-        const int pa = __ldg(a.sub_pt + u), pb = __ldg(a.sub_pt + u + 1);
-        const int ia = __ldg(a.sub_iv + u), ni = min(__ldg(a.sub_iv + u + 1) - ia, kSub);
-        const int v0 = su << kSubShift;
-        const int nv = min(kSub, (int)V - v0);
-        for (int e = threadIdx.x; e < C * (kSub / 4); e += 32 * kHeavyWarps) sts_zero4(sbase + 16u * e);
-        // this warp's intervals: those whose first point falls into the warp's share of [pa, pb)
-        const int s_l = (lane < ni) ? __ldg(a.starts + ia + lane) : pb;
-        const int share = ((long long)(s_l - pa) * kHeavyWarps) / (pb - pa);
-        const unsigned mine = __ballot_sync(0xffffffffu, lane < ni && share == warp);
-        int p_lo = 0, p_hi = 0;
-        if (mine) {
-            const int first = __ffs(mine) - 1, last = 31 - __clz(mine);
-            p_lo = __shfl_sync(0xffffffffu, s_l, first);
-            p_hi = __shfl_sync(0xffffffffu, s_l, min(last + 1, 31));
-            if (last + 1 >= ni) p_hi = pb;
-        }
-        __syncthreads();                                  // the stage is zeroed
-        if (mine)
-            reduce_points<NACC, EXACT, kHeavyU>(a, C, lane, p_lo, p_hi, b * (int)V, s_rx[warp], s_rd[warp],
-                                                sbase + ((unsigned)lane << 7), ((unsigned)lane & 7u) << 4);
-        __syncthreads();
-        // write-out: lane -> (row of a quad, 16-byte chunk); quads of rows are dealt to the warps
-        const int riq = lane >> 3, chunk = lane & 7;
-        float *blk = a.out + (int64_t)b * a.out_bstride + v0;
-        for (int r = 4 * warp + riq; r < C; r += 4 * kHeavyWarps) {
-            const int ck = (chunk - r) & 7;               // logical chunk held at smem position `chunk` of row r
-            const float4 x = lds_f4(sbase + ((unsigned)r << 7) + 16u * chunk);
-            if (4 * ck < nv) __stcs(reinterpret_cast<float4 *>(blk + (int64_t)r * V + 4 * ck), x);
-        }
-        __syncthreads();                                  // the stage is reused by the next queued sub-tile
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(a.heavy_ctl + 1, 1) == (int)gridDim.x - 1) {
-            a.heavy_ctl[0] = 0;
-            a.heavy_ctl[1] = 0;
-            a.heavy_ctl[2] = 0;
-            __threadfence();
         }
     }
 }
@@ -436,15 +394,8 @@ template <int NACC, bool EXACT, int LAYOUT>
 int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(a.B, n_ctas), 32, smem, stream>>>(a);
+    kern<<<dim3(a.B, n_ctas + a.front_y), 32, smem, stream>>>(a);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
-    if (a.heavy_list != nullptr) {
-        auto heavy = fwd_heavy_kernel<NACC, EXACT>;
-        if (smem > 48 * 1024)
-            FO_CUDA(cudaFuncSetAttribute(heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heavy<<<2 * sm_count(), 32 * kHeavyWarps, smem, stream>>>(a);
-        FO_LAUNCH_CHECK("fwd_heavy_kernel");
-    }
     return FO_OK;
 }
 template <int LAYOUT>
@@ -501,24 +452,14 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     a.out_rowstride = c_total;
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
 
-    // dense sub-tiles are queued for the multi-warp kernel when the block can be written with 128-bit stores
-    // ... and when a dense sub-tile's serial chain can be the launch's critical path: short launches (threshold 256
-    // points), or geometries with at least one frustum point per voxel on average (threshold 1024).  Measured on a
-    // B200 (us, inline -> queued): headline shape batch 1 / 2: 50 -> 37 / 67 -> 52; 512x1408 C = 32 batch 8:
-    // 398 -> 315; 512x1408 D = 118 C = 80 batch 1 / 2 / 8: 261 -> 128 / 328 -> 196 / 716 -> 627; at the headline
-    // shape, batch 8, the chains hide among 160 000 other sub-tiles and the second launch would cost 3-8 us.
-    const bool vec_ok = out_layout == FO_LAYOUT_BCZYX && (n_vox & 3) == 0 && interval_starts != nullptr;
-    const bool short_launch = (int64_t)B * n_vox * c * 4 <= kHeavyMaxOutBytes;
-    const bool dense_geometry = n_points >= (int64_t)B * n_vox;
-    const bool heavy_ok = vec_ok && (short_launch || dense_geometry);
-    a.heavy_pts = short_launch ? kHeavyPts : 4 * kHeavyPts;
-    a.sub_iv = pv.sub_iv;
-    a.heavy_list = heavy_ok ? pv.heavy_list : nullptr;
-    a.heavy_ctl = const_cast<FwdPlanHeader *>(pv.hdr)->fwd_heavy;
+    // dense sub-tiles go to the front CTAs (contiguous (B,C,Z,Y,X) output only)
+    const bool front_ok = out_layout == FO_LAYOUT_BCZYX && interval_starts != nullptr;
+    a.sub_iv = pv.sub_iv; a.iv_vox = pv.iv_vox; a.heavy_list = pv.heavy_list; a.n_heavy = pv.hdr->fwd_heavy;
+    a.front_y = front_ok ? (kFrontSlots + B - 1) / B : 0;
     const size_t smem = (size_t)kSub * c * sizeof(float);
     // 32-bit index arithmetic inside the kernel: feature rows * C and B*V must stay below 2^31 / 2^26
     const int n_ctas = sps;                                           // per sample (grid.y)
-    const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas <= 65535 && B <= 65535;
+    const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas + a.front_y <= 65535 && B <= 65535;
     if (dense_ok) {
         int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
                                                  : launch_dense_any<FO_LAYOUT_BZYXC>(a, n_ctas, smem, stream);
@@ -580,6 +521,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.n_points = INT_MAX - 1; a.n_intervals = n_intervals; a.n_intervals_dev = nullptr;
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
     a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
-    a.sub_iv = nullptr; a.heavy_list = nullptr; a.heavy_ctl = nullptr; a.heavy_pts = INT_MAX;
+    a.sub_iv = nullptr; a.iv_vox = nullptr; a.heavy_list = nullptr; a.n_heavy = nullptr; a.front_y = 0;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

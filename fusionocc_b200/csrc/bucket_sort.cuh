@@ -287,6 +287,11 @@ struct OrderArgs {
     // intervals longer than kLaneSortMax are queued here by the short pass and ordered, one warp each,
     // by the long pass — dense near-ego voxels are consecutive in voxel order, so without the queue a
     // few warps would inherit dozens of long intervals each (measured: 103 us -> tail-bound)
+    // forward plans: the order pass also lists the dense sub-tiles (nullptr to skip)
+    const int32_t *sub_pt;
+    int32_t n_subs;
+    int32_t *heavy_list;
+    int32_t *heavy_n;           // zero-initialised
     int32_t *long_list;
     int32_t *long_count;        // zero-initialised; [0] = intervals of kLaneSortMax+1 .. kWarpSortMax points,
                                 // [1] = longer ones, queued from the END of long_list (long_cap - 1 downwards)
@@ -317,6 +322,9 @@ template <bool kForward>
 __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
     const int n = *a.n_intervals;
     const int stride = gridDim.x * blockDim.x;
+    if (kForward && a.heavy_list != nullptr)
+        for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.n_subs; u += stride)
+            if (a.sub_pt[u + 1] - a.sub_pt[u] > kHeavyPts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         const int s = a.iv_starts[k], len = a.iv_lengths[k];
         if (len > kLaneSortMax) {

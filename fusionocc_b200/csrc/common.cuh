@@ -31,6 +31,7 @@ namespace fo {
 // coalesced instruction each and then walks them with lanes = channels (one 128-byte feature row per
 // point): ~230 instructions per sub-tile.
 // ----------------------------------------------------------------------------------------------
+constexpr int kHeavyPts     = 256;   // sub-tiles with more points are "dense": listed in the plan, split by the forward
 constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
 constexpr int kSubShift     = 5;
 #ifndef FO_TILE_THREADS
@@ -50,8 +51,7 @@ struct __align__(16) FwdPlanHeader {
     int32_t subs_per_sample;
     int32_t n_intervals;     // live count (copied from n_intervals_dev or the host argument)
     int32_t structured;      // 1: pt2vox / vox2iv are valid (plan produced by fo_rank_prepare)
-    int32_t fwd_heavy[3];    // forward: queue length of dense sub-tiles, heavy-kernel CTAs done, next queue entry
-                             // to hand out (all 0 between launches)
+    int32_t fwd_heavy[3];    // [0] number of dense sub-tiles listed in heavy_list (written when the plan is built)
     int32_t reserved[8];
 };
 static_assert(sizeof(FwdPlanHeader) == 64, "header is one 64-byte block");
@@ -72,7 +72,7 @@ __host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vo
 //   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | vox2iv[NV] | pos2iv[P_cap] | pt2vox[P_cap] | iv_vox[IV_cap]]
 //   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
 //   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
-//   heavy_list[]  per-launch queue of the forward: sub-tiles with more than 256 points
+//   heavy_list[]  the dense sub-tiles (more than kHeavyPts points), in no particular order
 //   vox2iv[v]     interval id of voxel v (rows of the backward's gathered out_grad); only when hdr.structured
 //   pos2iv[i]     interval id of sorted position i; only for plans built from caller-supplied intervals
 //   pt2vox[p]     voxel id of frustum point p, -1 if filtered; only when hdr.structured

@@ -228,6 +228,16 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
     }
 }
 
+// lists the dense sub-tiles of a plan built from caller-supplied intervals (the rank precompute does it inside
+// its order pass)
+__global__ void __launch_bounds__(256) heavy_queue_kernel(const int32_t *__restrict__ sub_pt, int n_subs,
+                                                          FwdPlanHeader *hdr, int32_t *heavy_list) {
+    if (hdr->flags & kFlagUnsorted) return;               // sub_pt is not meaningful then
+    const int stride = gridDim.x * blockDim.x;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_subs; u += stride)
+        if (sub_pt[u + 1] - sub_pt[u] > kHeavyPts) heavy_list[atomicAdd(hdr->fwd_heavy, 1)] = u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward plan, structured build (plans produced by fo_rank_prepare).
 // One warp per image pixel q = (b*N+n)*HW + hw: its <= D candidate points are p = ((b*N+n)*D + d)*HW + hw;
@@ -448,6 +458,8 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
         ranks_bev, interval_starts, interval_lengths, n_points, n_intervals, n_intervals_dev, n_vox,
         (int64_t)B * n_vox, sps, (int)n_subs, pv.hdr, pv.sub_iv, pv.sub_pt, pv.pos2iv, pv.iv_vox);
     FO_LAUNCH_CHECK("plan_from_intervals_kernel");
+    heavy_queue_kernel<<<grid_for(n_subs, 256, 4), 256, 0, stream>>>(pv.sub_pt, (int)n_subs, pv.hdr, pv.heavy_list);
+    FO_LAUNCH_CHECK("heavy_queue_kernel");
     return FO_OK;
 }
 
@@ -520,6 +532,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     oa.sorted = ranks_depth; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev;
+    oa.sub_pt = pv.sub_pt; oa.n_subs = (int32_t)n_subs; oa.heavy_list = pv.heavy_list; oa.heavy_n = pv.hdr->fwd_heavy;
     oa.dhw = make_fastdiv((uint32_t)(D * H * W)); oa.hw = make_fastdiv((uint32_t)(H * W));
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     oa.long_cap = (int32_t)P;
@@ -613,6 +626,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     OrderArgs oa;
     oa.sorted = order; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = iv_bucket; oa.n_intervals = counts_dev + 1;
+    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr;
     oa.ranks_feat = nullptr; oa.ranks_bev = sorted_keys;
     oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)n_points;
@@ -713,6 +727,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     OrderArgs oa;
     oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
     oa.n_intervals = &bv.hdr->n_bwd_intervals;
+    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr;
     oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = bv.slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)bv.cap;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
