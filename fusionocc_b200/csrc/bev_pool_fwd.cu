@@ -73,8 +73,14 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 #ifndef FO_FWD_MIN_CTAS
 #define FO_FWD_MIN_CTAS 32          // <= 64 registers: 32 single-warp CTAs per SM (the hardware's CTA limit)
 #endif
-constexpr int kFrontGroups = 8;     // a dense sub-tile is split into this many front CTAs
-constexpr int kFrontSlots  = 4096;  // front CTAs per launch (they loop over the list)
+#ifndef FO_FRONT_GROUPS
+#define FO_FRONT_GROUPS 8
+#endif
+#ifndef FO_FRONT_SLOTS
+#define FO_FRONT_SLOTS 4096
+#endif
+constexpr int kFrontGroups = FO_FRONT_GROUPS;     // a dense sub-tile is split into this many front CTAs
+constexpr int kFrontSlots  = FO_FRONT_SLOTS;  // front CTAs per launch (they loop over the list)
 
 // The reduction of one warp: points [p_lo, p_hi) of the sorted rank arrays, all inside one sub-tile, are
 // accumulated voxel by voxel — psum = fmaf(feat, depth, psum) from +0.0f in point order, the reference's

@@ -31,7 +31,10 @@ namespace fo {
 // coalesced instruction each and then walks them with lanes = channels (one 128-byte feature row per
 // point): ~230 instructions per sub-tile.
 // ----------------------------------------------------------------------------------------------
-constexpr int kHeavyPts     = 256;   // sub-tiles with more points are "dense": listed in the plan, split by the forward
+#ifndef FO_HEAVY_PTS
+#define FO_HEAVY_PTS 256
+#endif
+constexpr int kHeavyPts     = FO_HEAVY_PTS;   // sub-tiles with more points are "dense": listed in the plan, split by the forward
 constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
 constexpr int kSubShift     = 5;
 #ifndef FO_TILE_THREADS
