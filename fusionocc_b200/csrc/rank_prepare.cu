@@ -667,7 +667,10 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
                      (long long)fv.p_cap, (long long)n_depth);
         const int R = (D + 31) / 32;
         if (R > 8) return set_error(FO_ERR_UNSUPPORTED, "structured backward plan supports D <= 256 (got %d)", D);
-        const int blocks = grid_for(n_feat_rows * 32, 256, 8);
+        #ifndef FO_PLAN_CTAS_PER_SM
+#define FO_PLAN_CTAS_PER_SM 32     // one pixel per warp, many short CTAs: 125 -> 111 us at 512x1408 (8 -> 32)
+#endif
+        const int blocks = grid_for(n_feat_rows * 32, 256, FO_PLAN_CTAS_PER_SM);
         if (D <= 128 && (int64_t)B * n_vox < (1 << 24)) {   // packed-key bitonic variant
 #define FO_BITONIC(RR)                                                                                          \
     bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2vox, fv.vox2iv, D, hw,             \
