@@ -214,7 +214,10 @@ inline int sm_count() {
     return n;
 }
 
-inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = 8) {
+#ifndef FO_GRID_CTAS
+#define FO_GRID_CTAS 16
+#endif
+inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = FO_GRID_CTAS) {
     int64_t b = (work_items + per_block - 1) / per_block;
     const int64_t cap = 148 * (int64_t)ctas_per_sm;      // B200: 148 SMs
     if (b > cap) b = cap;

@@ -537,7 +537,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     oa.long_cap = (int32_t)P;
     const int64_t cap_iv = P < NV ? P : NV;
-    order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
+    order_short_kernel<true><<<grid_for(cap_iv, 256), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<fwd>");
     order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<fwd>");
@@ -631,7 +631,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)n_points;
     const int64_t cap_iv = n_points < n_buckets ? n_points : n_buckets;
-    order_short_kernel<true><<<grid_for(cap_iv, 256, 8), 256, 0, stream>>>(oa);
+    order_short_kernel<true><<<grid_for(cap_iv, 256), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<keys>");
     order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<keys>");
