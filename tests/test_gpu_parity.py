@@ -560,16 +560,18 @@ def test_batch32_shard_matches_single_sample_runs():
         assert torch.equal(f.grad[0].view(torch.int32), feat.grad[b].view(torch.int32)), f'sample {b}: feat_grad'
 
 
-@pytest.mark.parametrize('grid,C,B', [((7, 5, 3), 5, 3), ((1, 1, 1), 32, 2), ((9, 2, 2), 36, 1), ((33, 1, 1), 8, 2)])
-def test_odd_grids_take_the_scalar_paths(grid, C, B):
+@pytest.mark.parametrize('grid,C,B,D', [((7, 5, 3), 5, 3, 7), ((1, 1, 1), 32, 2, 7), ((9, 2, 2), 36, 1, 7),
+                                        ((33, 1, 1), 8, 2, 7), ((7, 5, 3), 12, 2, 120), ((1, 1, 1), 32, 1, 60)])
+def test_odd_grids_take_the_scalar_paths(grid, C, B, D):
     """Voxel counts that are not a multiple of 4 / 32 (ragged last sub-tile, no 128-bit stores or loads), one-voxel
     grids and channel counts that are not a multiple of 4: ranks exact, forward and both gradients bit-exact vs the
-    oracle, for the gradient of bev_pool_v2's output and for a channels-last gradient."""
+    oracle, for the gradient of bev_pool_v2's output and for a channels-last gradient; the dense cases put more than
+    256 points into a sub-tile, so the forward's front CTAs write ragged, unaligned voxel columns."""
     from fusionocc_b200.bev_pool import bev_pool_v2_with_plan
     from fusionocc_b200.view_transformer import rank_prepare
     from oracle import kernels as ok, rank_oracle as ro
     X, Y, Z = grid
-    N, D, H, W = 2, 7, 3, 5
+    N, H, W = 2, 3, 5                            # D = 120 / 60: > 256 points per sub-tile -> the front CTAs, ragged
     g = torch.Generator().manual_seed(X * 100 + Y * 10 + Z)
     lb = np.array([-1.0, -2.0, 0.5], np.float32)
     itv = np.array([0.5, 0.25, 1.0], np.float32)
