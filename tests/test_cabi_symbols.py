@@ -69,3 +69,17 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, os.path.join(dirpath, fn)
+
+
+def test_binding_argument_counts_match_the_header():
+    """Every ctypes signature has as many arguments as the prototype in include/fusionocc_b200.h (a drifted
+    binding would corrupt the call silently)."""
+    from fusionocc_b200 import _cabi
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = dict(re.findall(r'\b(fo_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S))
+    assert sorted(protos) == sorted(_cabi.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ('', 'void') else len([p for p in params.split(',') if p.strip()])
+        assert n == len(_cabi.SIGNATURES[name][1]), f'{name}: header has {n} parameters, binding {len(_cabi.SIGNATURES[name][1])}'
