@@ -21,7 +21,6 @@ is no CPU path: non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes
-from collections import OrderedDict
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -29,8 +28,8 @@ import torch
 from . import _cabi
 from ._cabi import FO_LAYOUT_BCZYX, FO_LAYOUT_BZYXC
 
-__all__ = ['bev_pool_v2', 'bev_pool_v2_cat', 'TRTBEVPoolv2', 'QuickCumsumCuda', 'VoxelPoolPlan', 'build_plan',
-           'clear_plan_cache']
+__all__ = ['bev_pool_v2', 'bev_pool_v2_cat', 'TRTBEVPoolv2', 'TRTBEVPoolv2Z', 'QuickCumsumCuda', 'VoxelPoolPlan', 'build_plan',
+           'attach_plan', 'clear_plan_cache']
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -66,6 +65,9 @@ class VoxelPoolPlan:
         self.fwd = fwd                      # uint8 plan buffer (its size fixes the layout)
         self.bwd: Optional[torch.Tensor] = None
         self.bwd_rows = -1
+        self.bwd_key = None
+        self._scratch: Optional[torch.Tensor] = None
+        self._scratch_key = None
         self.B, self.n_vox = B, n_vox
         self.n_points, self.n_intervals = n_points, n_intervals     # capacities when counts_dev is set
         self.counts_dev = counts_dev        # int32[4] {n_kept, n_intervals, 0, 0} or None
@@ -86,12 +88,16 @@ class VoxelPoolPlan:
         return int(self.fwd[:4].view(torch.int32).item())
 
     def ensure_bwd(self, ranks_depth: torch.Tensor, ranks_feat: torch.Tensor, n_depth: int,
-                   n_feat_rows: int) -> torch.Tensor:
-        if self.bwd is None or self.bwd_rows != n_feat_rows:
+                   n_feat_rows: int, sig=None) -> torch.Tensor:
+        """The inverse interval ordering.  It bakes ``ranks_depth`` in, so it is rebuilt whenever the
+        ``ranks_depth`` / ``ranks_feat`` the caller passes (``sig``: identity, version counter, address) or the
+        depth / feature sizes differ from the ones it was built for."""
+        structured = (self.structured_hw > 0 and self.n_depth == n_depth and n_feat_rows % self.structured_hw == 0
+                      and n_depth % n_feat_rows == 0 and n_depth // n_feat_rows <= 256)
+        key = (n_depth, n_feat_rows) if structured else (n_depth, n_feat_rows, sig)
+        if self.bwd is None or self.bwd_key != key:
             lib = _cabi.load()
             dev = ranks_feat.device
-            structured = (self.structured_hw > 0 and self.n_depth == n_depth and n_feat_rows % self.structured_hw == 0
-                          and n_depth % n_feat_rows == 0 and n_depth // n_feat_rows <= 256)
             cap = n_depth if structured else self.n_points
             nbytes = lib.fo_bwd_plan_bytes(cap, n_feat_rows)
             buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -101,8 +107,17 @@ class VoxelPoolPlan:
                     n_feat_rows, self.structured_hw if structured else 0,
                     _cabi.FO_BWD_PLAN_STRUCTURED if structured else 0, _p(self.fwd), self.fwd.numel(), self.B,
                     self.n_vox, _p(buf), nbytes), 'fo_bwd_plan_build')
-            self.bwd, self.bwd_rows = buf, n_feat_rows
+            self.bwd, self.bwd_key, self.bwd_rows = buf, key, n_feat_rows
         return self.bwd
+
+    def bwd_scratch(self, nbytes: int, device) -> torch.Tensor:
+        """Gather scratch of the backward, kept with the plan (it is sized by the plan's interval capacity, so
+        re-allocating it per call would cost ~380 MB of allocator traffic per backward at batch 8)."""
+        key = (torch.cuda.current_stream(device).cuda_stream, nbytes)
+        if self._scratch is None or self._scratch_key != key:
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._scratch_key = key
+        return self._scratch
 
 
 def build_plan(ranks_bev: torch.Tensor, interval_starts: torch.Tensor, interval_lengths: torch.Tensor,
@@ -121,29 +136,41 @@ def build_plan(ranks_bev: torch.Tensor, interval_starts: torch.Tensor, interval_
 
 
 # ---------------------------------------------------------------------------------------------
-# Plan cache: callers that pass the SAME index tensor objects again (accelerate mode, TRT-style
-# precomputed ranks) skip the plan kernels.  Entries hold strong references to the tensors, so an
-# id()/data_ptr can never be recycled while cached, and compare torch's in-place version counters.
+# Plan association.  Callers that pass the SAME index tensor objects again (accelerate mode, TRT-style
+# precomputed ranks, the tensors voxel_pooling_prepare_v2 just returned) skip the plan kernels: the plan is
+# ATTACHED to the caller's ranks_bev tensor object (a Python attribute), so it lives exactly as long as that
+# tensor does — no global table, no strong references to index tensors, nothing pinned after the caller drops
+# them.  A hit requires the same (ranks_bev, interval_starts, interval_lengths, ranks_feat) objects, unchanged
+# in place (torch's version counters) and at the same addresses; ranks_depth is part of the BACKWARD plan's key
+# (VoxelPoolPlan.ensure_bwd).  The key is taken from the tensors the caller passed, before any dtype
+# normalisation, so int64 callers hit as well.
 # ---------------------------------------------------------------------------------------------
-_PLAN_CACHE: 'OrderedDict[tuple, tuple]' = OrderedDict()
-_PLAN_CACHE_SIZE = 8
+def _sig(*tensors) -> tuple:
+    return tuple((id(t), t._version, t.data_ptr(), t.numel(), t.dtype) for t in tensors)
+
+
+def attach_plan(ranks_bev, interval_starts, interval_lengths, ranks_feat, plan: VoxelPoolPlan) -> None:
+    """Associate ``plan`` with these index tensors (used by the view transformer, whose rank precompute produces
+    the plan for free)."""
+    ranks_bev._fo_plan = (plan, _sig(ranks_bev, interval_starts, interval_lengths, ranks_feat) + (plan.B, plan.n_vox))
 
 
 def clear_plan_cache() -> None:
-    _PLAN_CACHE.clear()
+    """Kept for API compatibility: plans are attached to the caller's tensors and die with them."""
 
 
-def _cached_plan(rb, st, ln, rf, B, n_vox) -> VoxelPoolPlan:
-    key = (id(rb), id(st), id(ln), id(rf), B, n_vox)
-    ver = (rb._version, st._version, ln._version, rf._version, rb.data_ptr(), st.data_ptr(), ln.data_ptr())
-    hit = _PLAN_CACHE.get(key)
-    if hit is not None and hit[1] == ver:
-        _PLAN_CACHE.move_to_end(key)
+def _cached_plan(orig, rb, st, ln, B, n_vox) -> VoxelPoolPlan:
+    """``orig`` = the (ranks_bev, interval_starts, interval_lengths, ranks_feat) objects the caller passed;
+    ``rb/st/ln`` their int32 contiguous forms."""
+    key = _sig(*orig) + (B, n_vox)
+    hit = getattr(orig[0], '_fo_plan', None)
+    if hit is not None and hit[1] == key:
         return hit[0]
     plan = build_plan(rb, st, ln, B, n_vox)
-    _PLAN_CACHE[key] = (plan, ver, (rb, st, ln, rf))
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-        _PLAN_CACHE.popitem(last=False)
+    try:
+        orig[0]._fo_plan = (plan, key)
+    except Exception:  # noqa: BLE001 — an object that refuses attributes just rebuilds next time
+        pass
     return plan
 
 
@@ -180,18 +207,19 @@ def native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_sta
 
 def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, bev_feat_shape,
                     plan: VoxelPoolPlan, c_total: Optional[int] = None,
-                    c_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                    c_offset: int = 0, rank_sig=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """With ``c_total``, ``out_grad`` is the gradient of the WIDE tensor and only channels
     ``[c_offset, c_offset + C)`` of it are read."""
     lib = _cabi.load()
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
     dev = depth.device
     n_feat_rows = feat.numel() // C
-    bwd = plan.ensure_bwd(ranks_depth, ranks_feat, depth.numel(), n_feat_rows)
+    bwd = plan.ensure_bwd(ranks_depth, ranks_feat, depth.numel(), n_feat_rows,
+                          rank_sig if rank_sig is not None else _sig(ranks_depth, ranks_feat))
     depth_grad = torch.empty_like(depth)
     feat_grad = torch.empty_like(feat)
     sbytes = lib.fo_bwd_scratch_bytes(plan.n_intervals, C, og_layout)
-    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    scratch = plan.bwd_scratch(sbytes, dev)
     with torch.cuda.device(dev):
         if c_total is None:
             _cabi.check(lib.fo_bev_pool_v2_backward(
@@ -229,6 +257,8 @@ class QuickCumsumCuda(torch.autograd.Function):
     def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
                 interval_lengths, plan: Optional[VoxelPoolPlan] = None):
         _require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths)
+        orig = (ranks_bev, interval_starts, interval_lengths, ranks_feat)
+        ctx.rank_sig = _sig(ranks_depth, ranks_feat)
         # dtype / contiguity normalisation exactly as bev_pool.py:19-25
         ranks_bev = ranks_bev.int().contiguous()
         depth = depth.contiguous().float()
@@ -244,7 +274,7 @@ class QuickCumsumCuda(torch.autograd.Function):
         if feat.shape[-1] != C:
             raise ValueError(f'feat has {feat.shape[-1]} channels but bev_feat_shape says {C}')
         if plan is None:
-            plan = _cached_plan(ranks_bev, interval_starts, interval_lengths, ranks_feat, B, Z * Y * X)
+            plan = _cached_plan(orig, ranks_bev, interval_starts, interval_lengths, B, Z * Y * X)
         out = native_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
                              shape, plan)
         ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts, interval_lengths)
@@ -258,7 +288,7 @@ class QuickCumsumCuda(torch.autograd.Function):
         ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts, interval_lengths = ctx.saved_tensors
         out_grad, layout = _classify_out_grad(out_grad)
         depth_grad, feat_grad = native_backward(out_grad, layout, depth, feat, ranks_depth, ranks_feat,
-                                                ctx.bev_feat_shape, ctx.plan)
+                                                ctx.bev_feat_shape, ctx.plan, rank_sig=ctx.rank_sig)
         return depth_grad, feat_grad, None, None, None, None, None, None, None
 
 
@@ -287,10 +317,12 @@ class _PoolCat(torch.autograd.Function):
     def forward(ctx, bev_feat_shape, plans, *flat):
         n = len(flat) // 7
         B, Z, Y, X, _ = (int(s) for s in bev_feat_shape)
-        frames = []
+        frames, origs, sigs = [], [], []
         for i in range(n):
             depth, feat, rd, rf, rb, st, ln = flat[7 * i:7 * i + 7]
             _require_cuda(depth, feat, rd, rf, rb, st, ln)
+            origs.append((rb, st, ln, rf))
+            sigs.append(_sig(rd, rf))
             frames.append((depth.contiguous().float(), feat.contiguous().float(), rd.contiguous().int(),
                            rf.contiguous().int(), rb.int().contiguous(), st.contiguous().int(),
                            ln.contiguous().int()))
@@ -300,13 +332,13 @@ class _PoolCat(torch.autograd.Function):
         used, off = [], 0
         for i, (depth, feat, rd, rf, rb, st, ln) in enumerate(frames):
             plan = plans[i] if plans is not None and plans[i] is not None else \
-                _cached_plan(rb, st, ln, rf, B, Z * Y * X)
+                _cached_plan(origs[i], rb, st, ln, B, Z * Y * X)
             native_forward(depth, feat, rd, rf, rb, st, ln, (B, Z, Y, X, chans[i]), plan, out=out,
                            c_total=c_total, c_offset=off)
             used.append(plan)
             off += chans[i]
         ctx.save_for_backward(*[t for f in frames for t in f])
-        ctx.plans, ctx.chans, ctx.dims = used, chans, (B, Z, Y, X)
+        ctx.plans, ctx.chans, ctx.dims, ctx.sigs = used, chans, (B, Z, Y, X), sigs
         return out
 
     @staticmethod
@@ -327,7 +359,7 @@ class _PoolCat(torch.autograd.Function):
             depth, feat, rd, rf, rb, st, ln = saved[7 * i:7 * i + 7]
             if ctx.needs_input_grad[2 + 7 * i] or ctx.needs_input_grad[3 + 7 * i]:
                 dg, fg = native_backward(out_grad, layout, depth, feat, rd, rf, (B, Z, Y, X, c), ctx.plans[i],
-                                         c_total=c_total, c_offset=off)
+                                         c_total=c_total, c_offset=off, rank_sig=ctx.sigs[i])
             else:
                 dg = fg = None
             grads += [dg, fg, None, None, None, None, None]
@@ -372,4 +404,32 @@ class TRTBEVPoolv2(torch.autograd.Function):
                                interval_lengths)
         bev_feat = bev_feat.squeeze(2)
         bev_feat = bev_feat.permute(0, 2, 3, 1)
+        return bev_feat
+
+
+class TRTBEVPoolv2Z(torch.autograd.Function):
+    """LiCROcc's vendored variant of ``TRTBEVPoolv2``
+    (projects/LiCROcc/projects/mmdet3d_plugin/ops/bev_pool_v2/bev_pool.py:108-159): the grid height is an
+    argument (``output_z``, ONNX attributes ``output_height_i / output_width_i / output_z_i``), and only
+    ``output_z == 1`` is squeezed and permuted to ``(B,Y,X,C)``; otherwise the ``(B,C,Z,Y,X)`` tensor is
+    returned as it is."""
+
+    @staticmethod
+    def symbolic(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                 output_height=128, output_width=128, output_z=1):
+        return g.op('mmdeploy::bev_pool_v2', depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                    interval_lengths, output_height_i=output_height, output_width_i=output_width,
+                    output_z_i=output_z)
+
+    @staticmethod
+    def forward(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
+                output_height=128, output_width=128, output_z=1):
+        feat = feat.unsqueeze(0)
+        depth = depth.unsqueeze(0)
+        bev_feat_shape = (depth.shape[0], output_z, output_height, output_width, feat.shape[-1])   # (B, Z, Y, X, C)
+        bev_feat = bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                               interval_lengths)
+        if output_z == 1:
+            bev_feat = bev_feat.squeeze(2)
+            bev_feat = bev_feat.permute(0, 2, 3, 1)
         return bev_feat

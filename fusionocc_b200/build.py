@@ -17,16 +17,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libfusionocc_b200.so')
+# FUSIONOCC_LIB_SUFFIX builds a side-by-side variant (A/B measurements with FUSIONOCC_NVCC_EXTRA=-DFO_...=..)
+_SUFFIX = os.environ.get('FUSIONOCC_LIB_SUFFIX', '')
+LIB_PATH = os.path.join(LIB_DIR, f'libfusionocc_b200{_SUFFIX}.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 SOURCES = ['cabi.cu', 'rank_prepare.cu', 'bev_pool_fwd.cu', 'bev_pool_bwd.cu', 'lift_prepare.cu']
-HEADERS = ['common.cuh', 'bucket_sort.cuh']
+HEADERS = ['common.cuh', 'bucket_sort.cuh', 'tma.cuh']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-lineinfo', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-shared',
+    '-Xcompiler', '-fPIC',
     # no --use_fast_math: the voxel index needs IEEE div.rn / sub.rn
 ]
 
@@ -50,14 +52,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + '.tmp'
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-          ['-I', INCLUDE, '-o', tmp] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    obj_dir = os.path.join(LIB_DIR, 'obj' + _SUFFIX)
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    extra = (['-Xptxas', '-v'] if verbose else []) + os.environ.get('FUSIONOCC_NVCC_EXTRA', '').split()
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + extra + ['-I', INCLUDE, '-c', os.path.join(CSRC, src), '-o', obj]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    # one nvcc per translation unit, in parallel (the five files are independent; ~15 s instead of ~40 s)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for (obj, res), src in zip(results, SOURCES):
+        if verbose or res.returncode != 0:
+            sys.stderr.write(f'--- {src}\n' + res.stdout + res.stderr)
+    if any(res.returncode != 0 for _, res in results):
         raise RuntimeError('nvcc failed building libfusionocc_b200.so (see stderr)')
+    tmp = LIB_PATH + '.tmp'
+    res = subprocess.run([nvcc, '-shared', '-Xlinker', '-soname=libfusionocc_b200.so', '-o', tmp] +
+                         [obj for obj, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('linking libfusionocc_b200.so failed (see stderr)')
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -13,7 +13,10 @@
 //            pass staged through shared memory.  depth_grad[p] is the sequential FMA chain over
 //            c = 0..C-1 run by one thread, feat_grad[q, :] the sequential FMA over the pixel's points:
 //            the reference's exact orders, no atomics, every output written once.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace fo {
 
@@ -266,6 +269,278 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
     }
 }
 
+
+// =================================================================================================
+// Round-2 backward: one launch, two roles, no plan-sized or G-sized round trip through DRAM.
+//
+// (1) PIXEL ROLE, several pixels per warp.  A gathered out_grad row is C floats; with 128-bit accesses it needs
+//     only LPR = C/4 lanes (8 for C = 32), so one warp walks PPW = 32/LPR pixels in lock step and every row-loop
+//     instruction moves PPW rows (4 x 128 bytes at C = 32) — the per-point instruction count drops ~3x against the
+//     one-pixel-per-warp kernel above, which was latency/issue-bound (28 M warp instructions, 2.3 TB/s).
+//     feat_grad[q][4s..4s+3] stays ONE sequential FMA chain over the pixel's points in plan order in one thread,
+//     depth_grad[p] ONE sequential chain over c in one thread (bev_pool_cuda.cu:96-120): same bits as before.
+// (2) GATHER ROLE with TMA.  The C x 32 block of out_grad of a sub-tile is a regular 2-D tile: one
+//     cp.async.bulk.tensor (3-D map (V, C, B), box 32 x C x 1, 128-byte swizzle) per warp replaces 8 LDG.128 +
+//     8 STS.128 per lane and their address arithmetic, and is in flight while the warp fetches its interval list.
+// (3) NOT KEPT: one fused launch (gather units of sample b+1 interleaved with pixel units of sample b, device-side
+//     completion counters, G consumed while L2-resident).  Measured on a B200 at the headline shape, batch 8
+//     (profiles/r02_summary.md): two launches 163 us; fused and interleaved 225 us, with a two-stage box ring per
+//     gather warp 195 us, same kernel with all gather units first 184 us; spin waits were negligible (max 42 polls).
+//     The roles want different resources — the gather 6 CTAs x 8 warps at 24 registers to keep 6.5 TB/s of DRAM
+//     reads in flight, the pixel role 96 registers — and one kernel can only have the worse of both.
+// =================================================================================================
+constexpr int kPix2Threads = 128;            // threads per CTA of the multi-pixel kernel (short CTAs: finer tail)
+constexpr int kPix2Warps   = kPix2Threads / 32;
+constexpr int kRecCap      = 64;             // records of one pixel staged per chunk (longer pixels take several chunks)
+
+struct Pixel2Cfg {
+    int32_t tile_stride;   // floats per row of the per-warp tile rows[32][tile_stride]: C + 4 or C + 8 (conflict-free LDS.128)
+    int32_t warp_floats;   // floats of shared memory per warp
+};
+__host__ __device__ inline Pixel2Cfg pixel2_cfg(int C, int LPR) {
+    Pixel2Cfg c;
+    const int ppw = 32 / LPR;
+    c.tile_stride = ((C >> 2) & 1) ? C + 8 : C + 4;
+    // tile | feat rows of the PPW pixels | records (G row, depth bits) | depth indices
+    c.warp_floats = 32 * c.tile_stride + ppw * C + 2 * ppw * kRecCap + ppw * kRecCap;
+    return c;
+}
+
+// One warp, PPW = 32 / LPR backward intervals m0 .. m0 + PPW - 1 (lane group g = lane / LPR owns interval m0 + g).
+//   phase 1  ALL records of the pixels (up to kRecCap per chunk) are fetched at once — entry, then depth value:
+//            two dependent round trips per pixel instead of two per 8 points — and parked in shared memory;
+//   phase 2  tiles of LPR points per pixel: the gathered rows go into feat_grad's FMA chain and into the tile;
+//            the rows of the NEXT tile are requested before the depth-grad chains of the current one run.
+// FULL: C == 4 * LPR (every lane carries four channels).
+template <int LPR, bool FULL>
+__device__ __forceinline__ void pixel_warp(const PixelArgs &a, float *wsm, const int m0, const int n, const int lane) {
+    constexpr int PPW = 32 / LPR;
+    constexpr int U = LPR < 8 ? LPR : 8;          // rows in flight per lane (128-bit each)
+    const int g = lane / LPR, s = lane - g * LPR;
+    const int C = FULL ? 4 * LPR : a.C, c4 = C >> 2;
+    const Pixel2Cfg cfg = pixel2_cfg(C, LPR);
+    const int S = cfg.tile_stride;
+    float *rows = wsm;                                           // [32][S]
+    float *fs = rows + 32 * S;                                   // [PPW][C]
+    int2 *rec = reinterpret_cast<int2 *>(fs + PPW * C) + g * kRecCap;             // [PPW][kRecCap] (G row | -1, depth bits)
+    int *recp = reinterpret_cast<int *>(fs + PPW * C + 2 * PPW * kRecCap) + g * kRecCap;   // [PPW][kRecCap] depth index
+    const unsigned rows_s = (unsigned)__cvta_generic_to_shared(rows);
+    const unsigned fs_s = (unsigned)__cvta_generic_to_shared(fs + g * C);
+    const bool chan_ok = FULL || 4 * s < C;
+    const int n_depth = (int)a.n_depth, n_rows_G = (int)a.n_rows_G, n_iv = (int)a.n_iv;
+
+    const int m = m0 + g;
+    int st = 0, len = 0, q = -1;
+    if (m < n) {
+        st = __ldg(a.bwd_starts + m); len = __ldg(a.bwd_lengths + m); q = __ldg(a.bwd_ids + m);
+        if (len <= 0 || st < 0 || (int64_t)st + len > a.n_entries || q < 0 || q >= a.n_feat_rows) { len = 0; q = -1; }
+    }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    if (maxlen == 0) return;                                     // (feat_grad / depth_grad were zero-filled)
+    const int32_t *ep = a.ent_p + st, *ei = a.ent_iv + st;
+    // C == 32: every lane keeps its pixel's whole feature row in registers (the depth-grad chains then read only the
+    // tile: the broadcast LDS.128 of the row were a third of the kernel's shared-memory wavefronts, and the L1 data
+    // pipe is what bounds it — ncu, profiles/r02_summary.md); wider rows stay in shared memory
+    constexpr bool FREG = FULL && LPR == 8;
+    float4 fr[FREG ? LPR : 1];
+    if (FREG) {
+#pragma unroll
+        for (int i = 0; i < (FREG ? LPR : 1); ++i)
+            fr[i] = q >= 0 ? ldg4(a.feat + q * C + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (q >= 0 && chan_ok) {
+        reinterpret_cast<float4 *>(fs + g * C)[s] = ldg4(a.feat + q * C + 4 * s);
+    }
+    float4 fg = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *Gs = a.G + 4 * s;
+    const unsigned tile_col = rows_s + 4u * (unsigned)((g * LPR) * S + 4 * s);   // row g*LPR, my 4 channels
+    auto load_row = [&](int row) -> float4 {
+        const float *src = Gs + max(row, 0) * a.g_rowstride;     // invalid records read row 0 and are discarded
+        if (!chan_ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return ldg4(src);
+    };
+
+    for (int base = 0; base < maxlen; base += kRecCap) {
+        const int cnt = min(kRecCap, maxlen - base);             // warp-uniform
+        __syncwarp();                                            // the previous chunk is done with rec / recp
+        // ---- phase 1: records of this chunk
+        constexpr int RB = 4;
+        for (int i0 = 0; i0 < cnt; i0 += LPR * RB) {
+            int p[RB], row[RB];
+#pragma unroll
+            for (int k = 0; k < RB; ++k) {
+                const int i = base + i0 + s + LPR * k;
+                p[k] = -1; row[k] = -1;
+                if (i < len) { p[k] = __ldg(ep + i); row[k] = __ldg(ei + i); }
+            }
+            if (a.row_map) {
+#pragma unroll
+                for (int k = 0; k < RB; ++k) row[k] = ((unsigned)row[k] < (unsigned)n_iv) ? __ldg(a.row_map + row[k]) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < RB; ++k) {
+                const bool ok = (unsigned)p[k] < (unsigned)n_depth && (unsigned)row[k] < (unsigned)n_rows_G;
+                const float d = ok ? __ldg(a.depth + p[k]) : 0.f;
+                const int i = i0 + s + LPR * k;
+                if (i < kRecCap) {
+                    rec[i] = make_int2(ok ? row[k] : -1, __float_as_int(d));
+                    recp[i] = ok ? p[k] : -1;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: tiles of LPR points per pixel, rows of the next tile in flight during the chains
+        float4 x[U];
+        int2 r[U];
+#pragma unroll
+        for (int t = 0; t < U; ++t) { r[t] = rec[t]; x[t] = load_row(r[t].x); }
+        for (int j0 = 0; j0 < cnt; j0 += LPR) {
+#pragma unroll
+            for (int t0 = 0; t0 < LPR; t0 += U) {
+                if (t0 > 0) {                                    // LPR > U: later row groups of this tile
+#pragma unroll
+                    for (int t = 0; t < U; ++t) { r[t] = rec[j0 + t0 + t]; x[t] = load_row(r[t].x); }
+                }
+#pragma unroll
+                for (int t = 0; t < U; ++t) {
+                    if (chan_ok) sts_f4(tile_col + 4u * (unsigned)((t0 + t) * S), x[t]);
+                    const float d = __int_as_float(r[t].y);
+                    const float4 y = make_float4(fmaf(x[t].x, d, fg.x), fmaf(x[t].y, d, fg.y), fmaf(x[t].z, d, fg.z),
+                                                 fmaf(x[t].w, d, fg.w));
+                    if (r[t].x >= 0) fg = y;
+                }
+            }
+            const int my_p = recp[j0 + s];
+            if (j0 + LPR < cnt) {                                // first row group of the next tile
+#pragma unroll
+                for (int t = 0; t < U; ++t) { r[t] = rec[j0 + LPR + t]; x[t] = load_row(r[t].x); }
+            }
+            __syncwarp();
+            // depth grad: lane owns tile row `lane` = its own record; one sequential chain over all C channels
+            if (my_p >= 0) {
+                const unsigned ra = rows_s + 4u * (unsigned)(lane * S);
+                float sum = 0.f;
+                if (FREG) {                                      // the pixel's feature row lives in registers
+#pragma unroll
+                    for (int i = 0; i < (FREG ? LPR : 1); ++i) {
+                        const float4 gg = lds_f4(ra + 16u * i);
+                        sum = fmaf(gg.x, fr[i].x, sum);
+                        sum = fmaf(gg.y, fr[i].y, sum);
+                        sum = fmaf(gg.z, fr[i].z, sum);
+                        sum = fmaf(gg.w, fr[i].w, sum);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < c4; ++i) {
+                        const float4 gg = lds_f4(ra + 16u * i), f = lds_f4(fs_s + 16u * i);
+                        sum = fmaf(gg.x, f.x, sum);
+                        sum = fmaf(gg.y, f.y, sum);
+                        sum = fmaf(gg.z, f.z, sum);
+                        sum = fmaf(gg.w, f.w, sum);
+                    }
+                }
+                a.depth_grad[my_p] = sum;
+            }
+            __syncwarp();                                        // the tile is free for the next rows
+        }
+    }
+    if (q >= 0 && chan_ok) *reinterpret_cast<float4 *>(a.feat_grad + q * C + 4 * s) = fg;
+}
+
+#ifndef FO_PIX2_MINB
+#define FO_PIX2_MINB 4
+#endif
+template <int LPR, bool FULL>
+__global__ void __launch_bounds__(kPix2Threads, FO_PIX2_MINB) bwd_pixel2_kernel(PixelArgs a) {
+    extern __shared__ __align__(16) float psm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PPW = 32 / LPR;
+    const int n = a.n_bwd_dev ? min(max(*a.n_bwd_dev, 0), (int)a.n_bwd) : (int)a.n_bwd;
+    const int m0 = (blockIdx.x * kPix2Warps + warp) * PPW;
+    if (m0 >= n) return;
+    pixel_warp<LPR, FULL>(a, psm + warp * pixel2_cfg(a.C, LPR).warp_floats, m0, n, lane);
+}
+
+// Gather role of one warp: sub-tile su of sample b.  `stage` is 1024-byte aligned, C rows of 128 bytes.
+// Split in two so that a warp can have the boxes of several sub-tiles in flight before it consumes the first.
+struct GatherTile {
+    int ia, ni, my_v;
+};
+template <int NACC, bool EXACT>
+__device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensorMap *tm, float *stage, const unsigned bar,
+                                             const int b, const int su, const int lane, GatherTile &t) {
+    const int C = EXACT ? 32 * NACC : a.C;
+    t.ni = 0;
+    if (su >= a.sps) return false;
+    const int u = b * a.sps + su;
+    const int ia = __ldg(a.sub_iv + u), ib = __ldg(a.sub_iv + u + 1);
+    if (ib <= ia) return false;
+    const int v0 = su << kSubShift;
+    if (lane == 0) {
+        mbar_expect_tx(bar, (unsigned)C * 128u);
+        tma_load_3d((unsigned)__cvta_generic_to_shared(stage), tm, v0, 0, b, bar);
+    }
+    const int nv = (int)min((int64_t)kSub, a.V - v0);
+    const int vbase = (int)((int64_t)b * a.V) + v0;
+    t.ia = ia;
+    t.ni = min(ib - ia, kSub);
+    t.my_v = -1;
+    if (lane < t.ni) {
+        t.my_v = __ldg(a.iv_vox + ia + lane) - vbase;
+        if ((unsigned)t.my_v >= (unsigned)nv) t.my_v = -1;
+    }
+    return true;
+}
+template <int NACC, bool EXACT>
+__device__ __forceinline__ void gather_emit(const GatherArgs &a, const float *stage, const unsigned bar,
+                                            const unsigned parity, const int lane, const GatherTile &t) {
+    const int C = EXACT ? 32 * NACC : a.C;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+    float *dst = a.G + (int64_t)t.ia * C + lane;
+    mbar_wait(bar, parity);
+    for (int l = 0; l < t.ni; ++l, dst += C) {
+        const int v = __shfl_sync(0xffffffffu, t.my_v, l);
+        if (v < 0) continue;                         // warp-uniform
+#pragma unroll
+        for (int k = 0; k < NACC; ++k)
+            if (EXACT || lane + 32 * k < C) dst[32 * k] = lds_f32(sbase + swz_off(lane + 32 * k, v));
+    }
+}
+
+template <int NACC, bool EXACT>
+__global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const __grid_constant__ CUtensorMap tm) {
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    __shared__ __align__(8) unsigned long long s_bar[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (__ldg(&a.hdr->flags) & kFlagUnsorted) return;            // the per-interval gather runs instead
+    const int C = EXACT ? 32 * NACC : a.C;
+    const unsigned stage_bytes = ((unsigned)C * 128u + 1023u) & ~1023u;
+    unsigned char *base = (unsigned char *)(((uintptr_t)gsm + 1023) & ~(uintptr_t)1023);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    float *stage = reinterpret_cast<float *>(base + warp * stage_bytes);
+    GatherTile t;
+    if (gather_issue<NACC, EXACT>(a, &tm, stage, bar, blockIdx.y, blockIdx.x * 8 + warp, lane, t))
+        gather_emit<NACC, EXACT>(a, stage, bar, 0, lane, t);
+}
+
+// Order-agnostic gather for plans whose interval list is not canonical (kFlagUnsorted): one warp per interval,
+// G[k, :] = out_grad[b, :, voxel(k)]; intervals without a valid voxel get a zero row (never read: their points
+// carry row -1).
+__global__ void __launch_bounds__(256) bwd_gather_flagged_kernel(GatherArgs a, int64_t n_intervals) {
+    if (!(a.hdr->flags & kFlagUnsorted)) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = min((int64_t)max(a.hdr->n_intervals, 0), n_intervals);
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp0; k < n; k += nwarps) {
+        const int v = a.iv_vox[k];
+        const int64_t b = v >= 0 ? v / a.V : 0, vin = v >= 0 ? v - b * a.V : 0;
+        for (int c = lane; c < a.C; c += 32)
+            a.G[k * a.C + c] = v >= 0 ? a.og[b * a.og_bstride + (int64_t)c * a.V + vin] : 0.f;
+    }
+}
+
 // Scalar path (any C): one warp per backward interval.
 __global__ void __launch_bounds__(kPixThreads) bwd_pixel_scalar_kernel(PixelArgs a) {
     const int lane = threadIdx.x & 31;
@@ -394,6 +669,38 @@ int launch_pixel(const PixelArgs &pa, bool vec, cudaStream_t stream) {
 }  // namespace
 
 namespace {
+// FO_BWD_IMPL (debug / A-B measurements): 0 = round-1 kernels, 1 (default) = TMA gather + multi-pixel kernel
+int bwd_impl_choice() {
+    const char *e = getenv("FO_BWD_IMPL");
+    return (e && *e) ? atoi(e) : 1;
+}
+
+int launch_pixel2(const PixelArgs &pa, cudaStream_t stream) {
+    const int64_t pixels = pa.n_bwd;
+    if (pixels <= 0) return FO_OK;
+    const int C = pa.C;
+    const int lpr = C <= 32 ? 8 : (C <= 64 ? 16 : 32);
+    const int ppw = 32 / lpr;
+    const size_t smem = (size_t)kPix2Warps * pixel2_cfg(C, lpr).warp_floats * sizeof(float);
+    const int64_t blocks = (pixels + kPix2Warps * ppw - 1) / (kPix2Warps * ppw);
+    if (blocks >= INT_MAX) return set_error(FO_ERR_UNSUPPORTED, "too many backward intervals");
+#define FO_PIX2(L, F)                                                                                             \
+    do {                                                                                                          \
+        if (smem > 48 * 1024)                                                                                     \
+            FO_CUDA(cudaFuncSetAttribute(bwd_pixel2_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        bwd_pixel2_kernel<L, F><<<(unsigned)blocks, kPix2Threads, smem, stream>>>(pa);                            \
+    } while (0)
+    const bool full = C == 4 * lpr;
+    if (lpr == 8) { if (full) FO_PIX2(8, true); else FO_PIX2(8, false); }
+    else if (lpr == 16) { if (full) FO_PIX2(16, true); else FO_PIX2(16, false); }
+    else { if (full) FO_PIX2(32, true); else FO_PIX2(32, false); }
+#undef FO_PIX2
+    FO_LAUNCH_CHECK("bwd_pixel2_kernel");
+    return FO_OK;
+}
+}  // namespace
+
+namespace {
 int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t og_layout, int32_t c_total,
                   int32_t c_offset, const float *depth, const float *feat, int64_t n_points, int64_t n_intervals,
                   int32_t B, int64_t n_vox, int64_t n_depth, int64_t n_feat_rows, float *depth_grad,
@@ -426,20 +733,57 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
     pa.n_depth = n_depth; pa.n_feat_rows = n_feat_rows; pa.n_entries = bv.cap; pa.n_iv = n_intervals;
     pa.C = c; pa.depth_grad = depth_grad; pa.feat_grad = feat_grad;
 
+    const int impl = bwd_impl_choice();
+    // the round-2 kernels: 128-bit rows (C % 4 == 0, C <= 128), 32-bit index arithmetic
+    const bool v2_ok = impl >= 1 && vec && c <= 128 && n_feat_rows * c < INT_MAX && n_feat_rows < INT_MAX / 2 &&
+                       bv.cap < INT_MAX;
     if (og_layout == FO_LAYOUT_BCZYX) {
         const size_t need = fo_bwd_scratch_bytes(n_intervals, c, og_layout);
         if (!scratch || scratch_bytes < need)
             return set_error(FO_ERR_SCRATCH, "backward scratch is %zu bytes, need %zu", scratch_bytes, need);
-        FO_CHECK_ARG(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
-        const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
-        if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
+        FO_CHECK_ARG(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+        float *G = (float *)scratch;
         GatherArgs ga;
         ga.og = out_grad + (int64_t)c_offset * n_vox; ga.og_bstride = (int64_t)c_total * n_vox; ga.C = c; ga.V = n_vox;
         ga.sps = sps;
-        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = (float *)scratch;
+        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = G;
+        pa.G = G; pa.row_map = nullptr; pa.n_rows_G = n_intervals; pa.g_rowstride = c;
+        if (c > 256 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "channel or batch count too large for the gather kernel");
+        // plans built from caller-supplied intervals may be flagged non-canonical on the device: the per-interval
+        // gather fills G then (it exits at once otherwise), and the sub-tile gathers exit
+        bwd_gather_flagged_kernel<<<grid_for(n_intervals * 32, 256, 8), 256, 0, stream>>>(ga, n_intervals);
+        FO_LAUNCH_CHECK("bwd_gather_flagged_kernel");
+        const bool tma = v2_ok && n_intervals * c < INT_MAX && tmap_ok(ga.og, n_vox, c, c_total);
+        if (tma) {
+            CUtensorMap tm;
+            if (int rc = make_voxel_tmap(&tm, ga.og, n_vox, c, c_total, B)) return rc;
+            const int nacc = (c + 31) / 32;
+            const bool exact = c % 32 == 0;
+            const size_t stage_bytes = ((size_t)c * 128 + 1023) & ~(size_t)1023;
+            const size_t g_smem = 8 * stage_bytes + 1024;
+            const int gu = (sps + 7) / 8;
+            if (g_smem <= 200 * 1024 && gu <= 65535) {
+#define FO_GTMA(NA, EX)                                                                                            \
+    do {                                                                                                           \
+        if (g_smem > 48 * 1024)                                                                                    \
+            FO_CUDA(cudaFuncSetAttribute(bwd_gather_tma_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)g_smem));                                                            \
+        bwd_gather_tma_kernel<NA, EX><<<dim3(gu, B), 256, g_smem, stream>>>(ga, tm);                               \
+    } while (0)
+                if (nacc == 1) { if (exact) FO_GTMA(1, true); else FO_GTMA(1, false); }
+                else if (nacc == 2) { if (exact) FO_GTMA(2, true); else FO_GTMA(2, false); }
+                else if (nacc == 3) { if (exact) FO_GTMA(3, true); else FO_GTMA(3, false); }
+                else { if (exact) FO_GTMA(4, true); else FO_GTMA(4, false); }
+#undef FO_GTMA
+                FO_LAUNCH_CHECK("bwd_gather_tma_kernel");
+                return launch_pixel2(pa, stream);
+            }
+        }
+        // round-1 sub-tile gather (LDG path): any V, any C <= 256
+        const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
+        if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
         const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
-        if (n_ctas > 65535 || B > 65535 || c > 256)
-            return set_error(FO_ERR_UNSUPPORTED, "grid or channel count too large for the gather kernel");
+        if (n_ctas > 65535) return set_error(FO_ERR_UNSUPPORTED, "grid too large for the gather kernel");
 #define FO_GATHER(NA, EX)                                                                                     \
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \
@@ -469,10 +813,11 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         }
 #undef FO_GATHER
         FO_LAUNCH_CHECK("bwd_gather_kernel");
-        pa.G = (const float *)scratch; pa.row_map = nullptr; pa.n_rows_G = n_intervals; pa.g_rowstride = c;
     } else {
         pa.G = out_grad + c_offset; pa.row_map = pv.iv_vox; pa.n_rows_G = (int64_t)B * n_vox; pa.g_rowstride = c_total;
     }
+    if (v2_ok && (((uintptr_t)pa.G & 15) == 0) && (pa.g_rowstride % 4 == 0) && pa.n_rows_G * pa.g_rowstride < INT_MAX)
+        return launch_pixel2(pa, stream);
     const bool pvec = vec && (((uintptr_t)pa.G & 15) == 0) && (pa.g_rowstride % 4 == 0);
     return launch_pixel(pa, pvec, stream);
 }

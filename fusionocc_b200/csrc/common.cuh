@@ -63,7 +63,8 @@ struct __align__(16) BwdPlanHeader {
     int32_t n_bwd_intervals; // live count of backward intervals (distinct ranks_feat values / pixels)
     int32_t n_points;        // live point count
     int32_t totals[2];       // scratch for the scan's totals
-    int32_t reserved[12];
+    int32_t structured;      // 1: interval m IS feature row m (fixed-stride rows of D entries, built per pixel)
+    int32_t reserved[11];
 };
 static_assert(sizeof(BwdPlanHeader) == 64, "header is one 64-byte block");
 

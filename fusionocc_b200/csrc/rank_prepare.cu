@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
+        hdr->structured = 1;
     }
     for (int q = warp0; q < n_rows; q += nwarps) {
         const int bn = q / HW, hw = q - bn * HW;
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
+        hdr->structured = 1;
     }
     for (int q = warp0; q < n_rows; q += nwarps) {
         const int bn = q / HW, hw = q - bn * HW;
@@ -451,6 +453,11 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
     if (int rc = open_fwd_plan(plan, plan_bytes, B, n_vox, n_points, &pv, &n_subs, &sps)) return rc;
     FO_CHECK_ARG(n_intervals <= pv.iv_cap, "n_intervals=%lld exceeds the plan's interval capacity %lld",
                  (long long)n_intervals, (long long)pv.iv_cap);
+    // a non-canonical interval list leaves (parts of) these tables unwritten: give them defined contents, so that
+    // nothing downstream can index with uninitialised values (the backward reads pos2iv for every point)
+    FO_CUDA(cudaMemsetAsync(pv.sub_iv, 0, (size_t)(n_subs + 1) * 4, stream));
+    FO_CUDA(cudaMemsetAsync(pv.sub_pt, 0, (size_t)(n_subs + 1) * 4, stream));
+    if (n_points > 0) FO_CUDA(cudaMemsetAsync(pv.pos2iv, 0xFF, (size_t)n_points * 4, stream));
     init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_subs, sps, (int)n_intervals);
     FO_LAUNCH_CHECK("init_fwd_header_kernel");
     const int64_t work = n_intervals > n_subs + 1 ? n_intervals : n_subs + 1;

@@ -30,8 +30,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .bev_pool import (VoxelPoolPlan, _PLAN_CACHE, _PLAN_CACHE_SIZE, _p, _stream, bev_pool_v2,
-                       bev_pool_v2_with_plan)
+from .bev_pool import VoxelPoolPlan, _p, _stream, attach_plan, bev_pool_v2, bev_pool_v2_with_plan
 
 try:  # optional mm* integration
     from mmengine.model import BaseModule as _Base          # type: ignore
@@ -258,11 +257,7 @@ class LSSViewTransformer(_Base):
         exact = VoxelPoolPlan(plan.fwd, plan.B, plan.n_vox, n_kept, n_iv)
         exact.trusted = True
         exact.structured_hw, exact.n_depth = plan.structured_hw, plan.n_depth
-        key = (id(rb), id(st), id(ln), id(rf), plan.B, plan.n_vox)
-        ver = (rb._version, st._version, ln._version, rf._version, rb.data_ptr(), st.data_ptr(), ln.data_ptr())
-        _PLAN_CACHE[key] = (exact, ver, (rb, st, ln, rf))
-        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-            _PLAN_CACHE.popitem(last=False)
+        attach_plan(rb, st, ln, rf, exact)
         return rb, rd, rf, st, ln
 
     # ------------------------------------------------------------------ a6 (:196-221)

@@ -1,11 +1,10 @@
-"""Drop-in overlay for ``projects/LiCROcc/projects/mmdet3d_plugin/ops/bev_pool_v2/bev_pool.py`` (the vendored copy).
-
-Copy this directory over ``mmdet3d/ops/bev_pool_v2/`` of a FusionOcc / BEVDet-family checkout (or put
-``overlay/`` ahead of it on ``sys.path``): every view transformer in the tree imports
-``from mmdet3d.ops.bev_pool_v2.bev_pool import bev_pool_v2`` (e.g.
-``projects/FusionOcc/fusionocc/necks/view_transformer.py:11``) and picks up the B200-native op with
-the unchanged signature.  The reference's pybind extension ``bev_pool_v2_ext`` is no longer needed.
+"""Drop-in overlay for ``projects/LiCROcc/projects/mmdet3d_plugin/ops/bev_pool_v2/bev_pool.py`` — LiCROcc's
+VENDORED copy of the op, which differs from ``mmdet3d/ops/bev_pool_v2/bev_pool.py`` in one place: its
+``TRTBEVPoolv2`` (:108-159) takes ``(output_height, output_width, output_z)``, exports the ONNX attributes
+``output_height_i / output_width_i / output_z_i`` and squeezes Z only when ``output_z == 1``.  This module hands
+out that signature under the vendored name; ``bev_pool_v2`` / ``QuickCumsumCuda`` are the common op.
 """
-from fusionocc_b200.bev_pool import QuickCumsumCuda, TRTBEVPoolv2, bev_pool_v2  # noqa: F401
+from fusionocc_b200.bev_pool import QuickCumsumCuda, bev_pool_v2  # noqa: F401
+from fusionocc_b200.bev_pool import TRTBEVPoolv2Z as TRTBEVPoolv2  # noqa: F401
 
 __all__ = ['bev_pool_v2', 'TRTBEVPoolv2']

@@ -260,6 +260,70 @@ def test_unsorted_and_duplicate_free_user_intervals_take_scatter_path():
     assert plan2.flags() == 0
 
 
+@pytest.mark.parametrize('order', ['reversed', 'shuffled'])
+def test_backward_with_non_canonical_user_intervals(order):
+    """the backward must not index the sub-tile tables of a plan the device flagged as
+    non-canonical.  The reference backward ignores the forward intervals altogether (bev_pool.py:44-83), so the
+    gradients for reversed / shuffled interval lists equal the ones for the canonical list."""
+    from fusionocc_b200 import bev_pool_v2
+    from oracle import kernels as ok
+    case = rig_case('tiny', 2)
+    rb, rd, rf, st, ln = case['ranks']
+    C = 32
+    depth, feat = _values(case, C)
+    X, Y, Z = (int(v) for v in case['gs'])
+    shape = (2, Z, Y, X, C)
+    if order == 'reversed':
+        perm = np.arange(len(st))[::-1].copy()
+    else:
+        perm = np.random.default_rng(3).permutation(len(st))
+    st_p, ln_p = st[perm].copy(), ln[perm].copy()
+    want = ok.bev_pool_v2(depth.numpy(), feat.numpy(), rd, rf, rb, shape, st_p, ln_p)
+    d = depth.to(dev()).requires_grad_()
+    f = feat.to(dev()).requires_grad_()
+    out = bev_pool_v2(d, f, t(rd), t(rf), t(rb), shape, t(st_p), t(ln_p))
+    assert_bit_equal(out, want, f'forward ({order} intervals)')
+    og = torch.randn(out.shape, generator=torch.Generator().manual_seed(11))
+    out.backward(og.to(dev()))
+    dg, fg = ok.bev_pool_v2_backward(og.numpy(), depth.numpy(), feat.numpy(), rd, rf, rb)
+    assert_bit_equal(d.grad, dg, f'depth_grad ({order} intervals)')
+    assert_bit_equal(f.grad, fg, f'feat_grad ({order} intervals)')
+
+
+def test_backward_plan_follows_ranks_depth():
+    """the cached backward plan bakes ranks_depth in.  The same (ranks_bev, starts, lengths,
+    ranks_feat) objects with ranks_depth edited IN PLACE, or with another ranks_depth tensor, must not reuse it."""
+    from fusionocc_b200 import bev_pool_v2
+    from oracle import kernels as ok
+    case = rig_case('tiny', 1)
+    rb, rd, rf, st, ln = case['ranks']
+    C = 8
+    depth, feat = _values(case, C)
+    X, Y, Z = (int(v) for v in case['gs'])
+    shape = (1, Z, Y, X, C)
+    trb, trf, tst, tln, trd = t(rb), t(rf), t(st), t(ln), t(rd)
+    og = torch.randn((1, C, Z, Y, X), generator=torch.Generator().manual_seed(4))
+    # a second, different but valid (collision-free) depth index per point: the same pixel, depth bins mirrored
+    HW = case['coor'].shape[3] * case['coor'].shape[4]
+    D = case['coor'].shape[2]
+    dbin = (rd // HW) % D
+    rd2 = (rd + (D - 1 - 2 * dbin) * HW).astype(rd.dtype)
+
+    def run(rd_tensor, rd_np):
+        d = depth.to(dev()).requires_grad_()
+        f = feat.to(dev()).requires_grad_()
+        out = bev_pool_v2(d, f, rd_tensor, trf, trb, shape, tst, tln)
+        out.backward(og.to(dev()))
+        dg, fg = ok.bev_pool_v2_backward(og.numpy(), depth.numpy(), feat.numpy(), rd_np, rf, rb)
+        assert_bit_equal(d.grad, dg, 'depth_grad')
+        assert_bit_equal(f.grad, fg, 'feat_grad')
+
+    run(trd, rd)
+    run(t(rd2), rd2)                         # another tensor object
+    trd.copy_(t(rd2))                        # the first object, edited in place
+    run(trd, rd2)
+
+
 def test_channels_last_out_grad_layout():
     """A (B,Z,Y,X,C)-contiguous upstream gradient (channels-last consumer) is read in place."""
     from fusionocc_b200.bev_pool import QuickCumsumCuda
@@ -327,6 +391,39 @@ def test_trt_bev_pool_v2():
     assert_bit_equal(out.permute(0, 3, 1, 2).contiguous(), want[:, :, 0], 'TRTBEVPoolv2')
 
 
+@pytest.mark.parametrize('OZ', [1, 3])
+def test_trt_bev_pool_v2_licrocc_variant(OZ):
+    """LiCROcc's vendored TRTBEVPoolv2 (projects/LiCROcc/.../bev_pool_v2/bev_pool.py:108-159): output_z argument,
+    squeeze + NHWC permute only for output_z == 1, (B,C,Z,Y,X) otherwise.  Imported through the overlay path."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'overlay', 'projects', 'LiCROcc',
+                        'projects', 'mmdet3d_plugin', 'ops', 'bev_pool_v2', 'bev_pool.py')
+    spec = importlib.util.spec_from_file_location('licrocc_bev_pool_gpu', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from oracle import kernels as ok
+    from oracle.rank_oracle import intervals_from_sorted
+    rng = np.random.default_rng(1)
+    N, D, H, W, C, OH, OW = 2, 3, 4, 5, 8, 12, 16
+    depth = rng.random((N, D, H, W), dtype=np.float32)
+    feat = rng.standard_normal((N, H, W, C)).astype(np.float32)
+    P = N * D * H * W
+    rd = np.nonzero(rng.random(P) < 0.7)[0].astype(np.int32)
+    rf = ((rd // (D * H * W)) * (H * W) + rd % (H * W)).astype(np.int32)
+    rb = rng.integers(0, OZ * OH * OW, size=rd.shape[0]).astype(np.int32)
+    order = np.argsort(rb, kind='stable')
+    rb, rd, rf = rb[order], rd[order], rf[order]
+    st, ln = intervals_from_sorted(rb)
+    out = mod.TRTBEVPoolv2.apply(t(depth), t(feat), t(rd), t(rf), t(rb), t(st), t(ln), OH, OW, OZ)
+    want = ok.bev_pool_v2(depth[None], feat[None], rd, rf, rb, (1, OZ, OH, OW, C), st, ln)   # (1,C,OZ,OH,OW)
+    if OZ == 1:
+        assert tuple(out.shape) == (1, OH, OW, C)
+        assert_bit_equal(out.permute(0, 3, 1, 2).contiguous(), want[:, :, 0], 'LiCROcc TRTBEVPoolv2 (Z=1)')
+    else:
+        assert tuple(out.shape) == (1, C, OZ, OH, OW)
+        assert_bit_equal(out, want, 'LiCROcc TRTBEVPoolv2 (Z=3)')
+
+
 # ------------------------------------------------------------------------------------------ module level
 @pytest.mark.parametrize('sync_free', [False, True])
 @pytest.mark.parametrize('collapse_z', [False, True])
@@ -363,7 +460,6 @@ def test_view_transformer_end_to_end_vs_torch_cpu_path(sync_free, collapse_z):
 
 def test_accelerate_mode_caches_ranks_and_plan():
     from fusionocc_b200 import LSSViewTransformer
-    from fusionocc_b200.bev_pool import _PLAN_CACHE
     from fusionocc_b200.rig import SHAPES, make_calibration, make_values
     sh = SHAPES['tiny']
     B = 1
@@ -378,9 +474,9 @@ def test_accelerate_mode_caches_ranks_and_plan():
     dd, ff = depth.to(dev()).view(-1, vt.D, H, W), feat.to(dev()).view(-1, sh.channels, H, W)
     a1, _ = vt.view_transform(inp, dd, ff)
     assert vt.initial_flag is False and vt.ranks_bev.dtype == torch.int32
-    n_cached = len(_PLAN_CACHE)
+    plan1 = vt.ranks_bev._fo_plan[0]                  # attached by the rank precompute, lives with the tensor
     a2, _ = vt.view_transform(inp, dd, ff)
-    assert len(_PLAN_CACHE) == n_cached, 'second accelerate call must hit the plan cache'
+    assert vt.ranks_bev._fo_plan[0] is plan1, 'second accelerate call must reuse the attached plan'
     b1, _ = vt2.view_transform(inp, dd, ff)
     # accelerate path squeezes Z (:305) — with Z>1 the shapes differ from the collapse path by design
     assert torch.equal(a1, a2)

@@ -101,6 +101,12 @@ def test_overlay_import_paths():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         assert mod.bev_pool_v2 is fusionocc_b200.bev_pool_v2
+        # LiCROcc's vendored TRTBEVPoolv2 has its own signature (bev_pool.py:108-159 of that project)
+        import inspect
+        assert mod.TRTBEVPoolv2 is not TRTBEVPoolv2
+        assert list(inspect.signature(mod.TRTBEVPoolv2.forward).parameters)[-3:] == \
+            ['output_height', 'output_width', 'output_z']
+        assert list(inspect.signature(TRTBEVPoolv2.forward).parameters)[-2:] == ['out_height', 'out_width']
     finally:
         sys.path.remove(os.path.join(ROOT, 'overlay'))
         for m in [k for k in sys.modules if k == 'mmdet3d' or k.startswith('mmdet3d.')]:
