@@ -3,6 +3,8 @@
 // Replaces projects/FusionOcc/fusionocc/necks/view_transformer.py:223-281 (voxel_pooling_prepare_v2)
 // and the backward re-sort of mmdet3d/ops/bev_pool_v2/bev_pool.py:47-57.  See bucket_sort.cuh for
 // the sort itself.  Every kernel here is HBM/L2-bound integer work; nothing is reshaped into GEMMs.
+#include <stdlib.h>
+
 #include "bucket_sort.cuh"
 
 namespace fo {
@@ -138,6 +140,10 @@ __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a, CalibArg
         a.slot[p] = k >= 0 ? atomicAdd(a.cnt + k, 1) : 0;
     }
 }
+
+}  // namespace fo
+#include "rank_chunk.cuh"
+namespace fo {
 
 // K1 (backward flavour): keys are given (ranks_feat of each forward position).
 __global__ void __launch_bounds__(256) count_keys_kernel(const int32_t *__restrict__ keys, int64_t n_cap,
@@ -472,7 +478,9 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
 
 extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total) {
     if (n_points_total < 0 || n_voxels_total < 0) return 0;
-    return bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256);
+    const size_t legacy = bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256);
+    const size_t chunked = chunk_scratch_view(nullptr, chunk_bound(n_voxels_total), n_points_total).total_bytes;
+    return legacy > chunked ? legacy : chunked;
 }
 
 namespace {
@@ -499,6 +507,63 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     FwdPlanView pv; int64_t n_subs; int sps;
     if (int rc = open_fwd_plan(fwd_plan, fwd_plan_bytes, B, n_vox, P, &pv, &n_subs, &sps)) return rc;
 
+    // ---- FO_RANK_IMPL=1: the two-level sort with chunks of 1024 voxels ordered in shared memory (rank_chunk.cuh);
+    //      same results, measured slower than the global bucket sort below on a B200 (see the header of that file),
+    //      so it is opt-in.
+    {
+        const char *re = getenv("FO_RANK_IMPL");
+        const int impl = (re && *re) ? atoi(re) : 0;
+        const ChunkGeom g = chunk_geom(n_vox, B);
+        if (impl >= 1 && g.cps <= kChunkMaxPerSample && g.n_chunks <= chunk_bound(NV) && B <= 65535) {
+            ChunkScratch sc = chunk_scratch_view(scratch, chunk_bound(NV), P);
+            FO_CUDA(cudaMemsetAsync(scratch, 0, sc.zero_bytes, stream));
+            FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
+            ChunkArgs ca;
+            VoxArgs &va = ca.vox;
+            va.coor = coor; va.n_points = P; va.points_per_sample = pps;
+            va.lbx = lower_bound[0]; va.lby = lower_bound[1]; va.lbz = lower_bound[2];
+            va.ivx = interval[0]; va.ivy = interval[1]; va.ivz = interval[2];
+            va.X = X; va.Y = Y; va.Z = Z;
+            va.cnt = nullptr; va.key = pv.pt2vox; va.slot = nullptr;
+            va.hdr = pv.hdr; va.n_subs = (int)n_subs; va.subs_per_sample = sps;
+            ca.calib = calib ? *calib : CalibArgs{};
+            ca.g = g; ca.B = B; ca.pps = pps; ca.n_cams = N; ca.dhw_pts = D * H * W;
+            ca.hist = sc.hist; ca.cursor = sc.cursor; ca.chunk_off = sc.chunk_off; ca.iv_off = sc.iv_off; ca.ctrl = sc.ctrl;
+            ca.list = sc.list; ca.list_m = sc.list_m; ca.list_l = sc.list_l; ca.counts = counts_dev;
+            ca.rb = ranks_bev; ca.rd = ranks_depth; ca.rf = ranks_feat;
+            ca.iv_starts = interval_starts; ca.iv_lengths = interval_lengths;
+            ca.sub_iv = pv.sub_iv; ca.sub_pt = pv.sub_pt; ca.heavy_list = pv.heavy_list; ca.vox2iv = pv.vox2iv;
+            ca.iv_vox = pv.iv_vox; ca.hdr = pv.hdr;
+            ca.dhw = make_fastdiv((uint32_t)(D * H * W)); ca.hw = make_fastdiv((uint32_t)(H * W));
+            ca.n_subs = (int)n_subs;
+            FO_CHECK_ARG((int64_t)B * N <= 65535, "B*N=%lld exceeds the grid bound", (long long)B * N);
+            const dim3 grid_a((unsigned)(((int64_t)D * H * W + kChunkBlockPts - 1) / kChunkBlockPts), (unsigned)(B * N));
+            const size_t smem_a = (size_t)g.cps * sizeof(int);
+            if (calib) chunk_voxelize_kernel<true><<<grid_a, kChunkThreads, smem_a, stream>>>(ca);
+            else chunk_voxelize_kernel<false><<<grid_a, kChunkThreads, smem_a, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_voxelize_kernel");
+            chunk_scatter_kernel<<<grid_a, kChunkThreads, smem_a, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_scatter_kernel");
+            chunk_distinct_kernel<<<(g.n_chunks + 7) / 8, kChunkThreads, 0, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_distinct_kernel");
+            const size_t smem_s = 4 * ((chunk_sort_smem(kClassS) + 15) / 16 * 16);
+            const size_t smem_m = chunk_sort_smem(kClassM), smem_l = chunk_sort_smem(kStageL);
+            // only the dense class needs more than the default 48 KB of dynamic shared memory
+            FO_CUDA(cudaFuncSetAttribute(chunk_sort_cta_kernel<16, kStageL, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            FO_CUDA(cudaFuncSetAttribute(chunk_sort_cta_kernel<8, kClassM, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+            // the dense classes first: their CTAs are the long ones
+            const int sms = sm_count();
+            chunk_sort_cta_kernel<16, kStageL, true><<<sms < g.n_chunks ? sms : g.n_chunks, 512, smem_l, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_sort_cta_kernel<large>");
+            chunk_sort_cta_kernel<8, kClassM, false><<<4 * sms < g.n_chunks ? 4 * sms : g.n_chunks, 256, smem_m, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_sort_cta_kernel<medium>");
+            chunk_sort_small_kernel<<<(g.n_chunks + 3) / 4, 128, smem_s, stream>>>(ca);
+            FO_LAUNCH_CHECK("chunk_sort_small_kernel");
+            return FO_OK;
+        }
+    }
     SortScratch ss = sort_scratch_view(scratch, NV);
     int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
     int32_t *key = pv.pt2vox;                    // voxel id of every frustum point, -1 if outside the grid

@@ -181,6 +181,33 @@ def test_rank_prepare_all_filtered_returns_nones():
     assert vt.voxel_pooling_prepare_v2(coor) == (None, None, None, None, None)
 
 
+@pytest.mark.parametrize('name,B', [('tiny', 2), ('small', 2), ('base', 2)])
+def test_chunk_sort_rank_pipeline_matches_the_default(name, B, monkeypatch):
+    """FO_RANK_IMPL=1 (two-level sort, 1024-voxel chunks ordered in shared memory, csrc/rank_chunk.cuh) produces the
+    same five rank arrays as the default global bucket sort, hence the reference's (both are checked against the
+    oracle here), from coor and from the calibration."""
+    from fusionocc_b200 import pack_calibration, rank_prepare, rank_prepare_calib
+    case = rig_case(name, B)
+    want = case['ranks']
+    lb, itv, gs = case['lb'].tolist(), case['itv'].tolist(), [int(v) for v in case['gs']]
+    coor = case['coor'].to(dev())
+    cal = [c.to(dev()) for c in case['calib']]
+    cam, bda12, has_t = pack_calibration(cal[0], cal[2], cal[3], cal[4], cal[5])
+    for impl in ('1', '0'):
+        monkeypatch.setenv('FO_RANK_IMPL', impl)
+        for mode in ('coor', 'calib'):
+            if mode == 'coor':
+                rb, rd, rf, st, ln, counts, plan = rank_prepare(coor, lb, itv, gs)
+            else:
+                rb, rd, rf, st, ln, counts, plan = rank_prepare_calib(case['frustum'].to(dev()), cam, bda12, has_t, B,
+                                                                      coor.shape[1], lb, itv, gs)
+            nk, ni = (int(v) for v in counts[:2].tolist())
+            assert (nk, ni) == (len(want[0]), len(want[3])), f'impl {impl} {mode}: counts'
+            for nm, a, b in zip(('ranks_bev', 'ranks_depth', 'ranks_feat', 'interval_starts', 'interval_lengths'),
+                                (rb[:nk], rd[:nk], rf[:nk], st[:ni], ln[:ni]), want):
+                assert np.array_equal(a.cpu().numpy(), b), f'impl {impl} {mode}: {nm} differs from the oracle'
+
+
 # ------------------------------------------------------------------------------------------ forward/backward
 def _values(case, C, seed=0):
     g = torch.Generator().manual_seed(seed)
