@@ -18,7 +18,7 @@ FO_LAYOUT_BCZYX = 0
 FO_LAYOUT_BZYXC = 1
 FO_FWD_ASSUME_SORTED = 1
 FO_BWD_PLAN_STRUCTURED = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _ERR_NAMES = {1: 'FO_ERR_INVALID_ARG', 2: 'FO_ERR_CUDA', 3: 'FO_ERR_UNSUPPORTED', 4: 'FO_ERR_SCRATCH'}
 
@@ -67,6 +67,11 @@ SIGNATURES = {
     'fo_compat_bev_pool_v2': (None, [c_int, c_int] + [c_void_p] * 8),
     'fo_compat_bev_pool_v2_grad': (None, [c_int, c_int] + [c_void_p] * 10),
     'fo_view_transform_host_workspace_bytes': (c_size_t, [c_int32] * 10),
+    'fo_view_transform_host_calib_workspace_bytes': (c_size_t, [c_int32] * 10),
+    'fo_view_transform_host_calib': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _f3, _f3,
+                                             c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_void_p]),
     'fo_view_transform_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, _f3, _f3, c_int32, c_int32, c_int32, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -83,13 +88,23 @@ def lib_path() -> str:
     return os.environ.get('FUSIONOCC_B200_LIB', _build.LIB_PATH)
 
 
+def _stale() -> bool:
+    try:
+        return _build.needs_build()
+    except OSError:          # sources not shipped next to the library: nothing to compare with
+        return False
+
+
 def load() -> ctypes.CDLL:
     """Load (building in-tree if necessary) the native library; raises if impossible."""
     global _lib
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.isfile(path):
+    # the in-tree library is rebuilt whenever a source or the header is newer than it (a stale .so would be called
+    # with argument lists that no longer match its prototypes); FUSIONOCC_B200_LIB pins an explicit file instead
+    stale = 'FUSIONOCC_B200_LIB' not in os.environ and os.path.isfile(path) and _stale()
+    if not os.path.isfile(path) or stale:
         try:
             path = _build.build()
         except Exception as e:  # noqa: BLE001

@@ -480,7 +480,7 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     else if (out_layout == FO_LAYOUT_BCZYX) { n_runs = B; run_len = (int64_t)c * n_vox; run_stride = a.out_bstride; }
     else { n_runs = (int64_t)B * n_vox; run_len = c; run_stride = c_total; }
     const int vec = (run_len % 4 == 0) && (run_stride % 4 == 0) && (((uintptr_t)a.out & 15) == 0);
-    zero_if_flag_kernel<<<148 * 8, 256, 0, stream>>>(a.out, n_runs, run_len, run_stride, vec, pv.hdr, need_flag);
+    zero_if_flag_kernel<<<sm_count() * 8, 256, 0, stream>>>(a.out, n_runs, run_len, run_stride, vec, pv.hdr, need_flag);
     FO_LAUNCH_CHECK("zero_if_flag_kernel");
     const int blocks = grid_for(n_intervals * 32, 256, 8);
     if (out_layout == FO_LAYOUT_BCZYX)

@@ -206,12 +206,14 @@ int set_error(int code, const char *fmt, ...);
 int open_fwd_plan_const(const void *plan, size_t plan_bytes, int32_t B, int64_t n_vox, int64_t n_points,
                         FwdPlanView *pv, int64_t *n_subs, int *sps);
 
-// number of SMs of the current device (148 on B200)
+// number of SMs of the current device (148 on B200), queried once per device
 inline int sm_count() {
+    static int cached[64] = {0};
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-        n = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
 }
 
@@ -220,7 +222,7 @@ inline int sm_count() {
 #endif
 inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = FO_GRID_CTAS) {
     int64_t b = (work_items + per_block - 1) / per_block;
-    const int64_t cap = 148 * (int64_t)ctas_per_sm;      // B200: 148 SMs
+    const int64_t cap = sm_count() * (int64_t)ctas_per_sm;   // a whole number of waves (148 SMs on a B200)
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }

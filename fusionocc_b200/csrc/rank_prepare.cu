@@ -611,7 +611,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     const int64_t cap_iv = P < NV ? P : NV;
     order_short_kernel<true><<<grid_for(cap_iv, 256), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<fwd>");
-    order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
+    order_long_kernel<true><<<sm_count() * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<fwd>");
     return FO_OK;
 }
@@ -705,7 +705,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     const int64_t cap_iv = n_points < n_buckets ? n_points : n_buckets;
     order_short_kernel<true><<<grid_for(cap_iv, 256), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<keys>");
-    order_long_kernel<true><<<148 * 16, kSortThreads, 0, stream>>>(oa);
+    order_long_kernel<true><<<sm_count() * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<keys>");
     return FO_OK;
 }
@@ -807,7 +807,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     oa.long_list = bv.slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)bv.cap;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_short_kernel<bwd>");
-    order_long_kernel<false><<<148 * 16, kSortThreads, 0, stream>>>(oa);
+    order_long_kernel<false><<<sm_count() * 16, kSortThreads, 0, stream>>>(oa);
     FO_LAUNCH_CHECK("order_long_kernel<bwd>");
     bwd_plan_fill_entries_kernel<<<grid_for(n_points, 256), 256, 0, stream>>>(bv.pos, ranks_depth, fv.pos2iv, bv.hdr,
                                                                               bv.cap, bv.ent_p, bv.ent_iv);

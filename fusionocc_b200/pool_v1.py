@@ -19,7 +19,10 @@ from __future__ import annotations
 import torch
 
 from . import _cabi
-from .bev_pool import _p, _require_cuda, _stream, bev_pool_v2
+import ctypes
+
+from .bev_pool import (FO_LAYOUT_BCZYX, FO_LAYOUT_BZYXC, VoxelPoolPlan, _p, _require_cuda, _stream, native_backward,
+                       native_forward)
 
 __all__ = ['bev_pool', 'occ_pool', 'rank_from_keys']
 
@@ -61,12 +64,52 @@ def bev_pool(feats: torch.Tensor, coords: torch.Tensor, B: int, D: int, H: int, 
     ok = (x >= 0) & (x < H) & (y >= 0) & (y < W) & (z >= 0) & (z < D) & (b >= 0) & (b < B)
     keys = torch.where(ok, ((b * D + z) * H + x) * W + y, torch.full_like(x, -1)).int()
     rb, order, st, ln, counts = rank_from_keys(keys, B * D * H * W)
-    n_kept, n_iv = (int(v) for v in counts[:2].tolist())      # like the reference's torch.where (bev_pool.py:46)
-    if n_kept == 0:
-        return feats.new_zeros((B, C, D, H, W), dtype=torch.float32)
-    rb, order, st, ln = rb[:n_kept], order[:n_kept], st[:n_iv], ln[:n_iv]
-    ones = torch.ones(feats.shape[0], dtype=torch.float32, device=feats.device)
-    return bev_pool_v2(ones, feats, order, order, rb, (B, D, H, W, C), st, ln)
+    # no host read-back: the live counts stay on the device (the reference syncs in torch.where, bev_pool.py:46)
+    n = feats.shape[0]
+    plan = build_plan_from_counts(rb, st, ln, counts, B, D * H * W, n)
+    return _UnitDepthPool.apply(feats, order, rb, st, ln, plan, (B, D, H, W, C))
+
+
+def build_plan_from_counts(rb, st, ln, counts, B: int, n_vox: int, n_points: int) -> VoxelPoolPlan:
+    """Forward plan over capacity-sized rank arrays whose live sizes are ``counts`` on the device."""
+    lib = _cabi.load()
+    dev = rb.device
+    cap_iv = st.numel()
+    nbytes = lib.fo_fwd_plan_bytes(B * n_vox, max(n_points, cap_iv))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.fo_fwd_plan_build(_stream(dev), _p(rb), _p(st), _p(ln), n_points, cap_iv,
+                                          ctypes.c_void_p(counts.data_ptr() + 4), B, n_vox, _p(buf), nbytes),
+                    'fo_fwd_plan_build')
+    return VoxelPoolPlan(buf, B, n_vox, n_points, cap_iv, counts_dev=counts)
+
+
+class _UnitDepthPool(torch.autograd.Function):
+    """Sum of pre-multiplied point features per voxel = bev_pool_v2 with a unit depth; the gradient w.r.t. the
+    (constant) depth vector is never formed into a tensor the caller sees."""
+
+    @staticmethod
+    def forward(ctx, feats, order, rb, st, ln, plan, shape):
+        feats32 = feats.contiguous().float()
+        ones = torch.ones(feats32.shape[0], dtype=torch.float32, device=feats32.device)
+        out = native_forward(ones, feats32, order, order, rb, st, ln, shape, plan)
+        ctx.save_for_backward(ones, feats32, order)
+        ctx.plan, ctx.shape, ctx.in_dtype = plan, shape, feats.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        ones, feats32, order = ctx.saved_tensors
+        if out_grad.dtype != torch.float32:
+            out_grad = out_grad.float()
+        if out_grad.is_contiguous():
+            layout = FO_LAYOUT_BCZYX
+        elif out_grad.permute(0, 2, 3, 4, 1).is_contiguous():
+            layout = FO_LAYOUT_BZYXC
+        else:
+            out_grad, layout = out_grad.contiguous(), FO_LAYOUT_BCZYX
+        _dg, fg = native_backward(out_grad, layout, ones, feats32, order, order, ctx.shape, ctx.plan)
+        return fg.to(ctx.in_dtype), None, None, None, None, None, None
 
 
 def occ_pool(feats: torch.Tensor, coords: torch.Tensor, B, D, H, W) -> torch.Tensor:

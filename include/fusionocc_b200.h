@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 1
+#define FO_ABI_VERSION 2
 
 #define FO_OK                  0
 #define FO_ERR_INVALID_ARG     1   /* null pointer, negative size, bad enum, misaligned buffer   */
@@ -324,6 +324,28 @@ int fo_view_transform_host(fo_stream_t stream,
                            int32_t counts_host[4],
                            void *workspace_dev, size_t workspace_bytes,
                            fo_stream_t upload_stream);
+
+/* Same, from the CALIBRATION instead of a materialised (B,N,D,H,W,3) point tensor: the rank precompute computes
+ * every frustum point from the per-camera matrices (fo_rank_prepare_calib), so the host uploads 0.74 MB of frustum
+ * template + 96 bytes per camera instead of 4.46 MB of points per sample.  Argument meaning as fo_rank_prepare_calib
+ * (frustum [D*H*W,3], cam_mats [B*N,24], bda [B,12]) and fo_view_transform_host. */
+size_t fo_view_transform_host_calib_workspace_bytes(int32_t B, int32_t N, int32_t D, int32_t H, int32_t W,
+                                                    int32_t c, int32_t X, int32_t Y, int32_t Z,
+                                                    int32_t with_backward);
+
+int fo_view_transform_host_calib(fo_stream_t stream,
+                                 const float *frustum_host, const float *cam_mats_host, const float *bda_host,
+                                 int32_t bda_has_translation, int32_t matvec_mode,
+                                 const float *depth_host, const float *feat_host,
+                                 const float *out_grad_host /* may be NULL: forward only */,
+                                 int32_t B, int32_t N, int32_t D, int32_t H, int32_t W, int32_t c,
+                                 const float lower_bound[3], const float interval[3],
+                                 int32_t X, int32_t Y, int32_t Z,
+                                 float *out_host /* (B,c,Z,Y,X) */,
+                                 float *depth_grad_host, float *feat_grad_host,
+                                 int32_t counts_host[4],
+                                 void *workspace_dev, size_t workspace_bytes,
+                                 fo_stream_t upload_stream);
 
 #ifdef __cplusplus
 }

@@ -199,7 +199,7 @@ def test_chunk_sort_rank_pipeline_matches_the_default(name, B, monkeypatch):
             if mode == 'coor':
                 rb, rd, rf, st, ln, counts, plan = rank_prepare(coor, lb, itv, gs)
             else:
-                rb, rd, rf, st, ln, counts, plan = rank_prepare_calib(case['frustum'].to(dev()), cam, bda12, has_t, B,
+                rb, rd, rf, st, ln, counts, plan = rank_prepare_calib(torch.as_tensor(case['frustum']).to(dev()), cam, bda12, has_t, B,
                                                                       coor.shape[1], lb, itv, gs)
             nk, ni = (int(v) for v in counts[:2].tolist())
             assert (nk, ni) == (len(want[0]), len(want[3])), f'impl {impl} {mode}: counts'
