@@ -66,7 +66,8 @@ def build(reference_root: str = '/root/reference', force: bool = False, which: s
         if not os.path.isfile(os.path.join(lib_dir, 'libfusionocc_b200.so')):
             raise FileNotFoundError('build libfusionocc_b200.so first (python -m fusionocc_b200.build)')
         sources = sources + [os.path.join(HERE, 'shim', 'bev_pool_shim.cpp')]
-        kw = dict(extra_include_paths=[os.path.join(ROOT, 'include')],
+        kw = dict(with_cuda=True,            # no .cu among the sources, but bev_pool.cpp includes the CUDA guard headers
+                  extra_include_paths=[os.path.join(ROOT, 'include')],
                   extra_ldflags=[f'-L{lib_dir}', '-lfusionocc_b200', f'-Wl,-rpath,{lib_dir}'])
     load(name=t['name'], sources=sources, extra_cuda_cflags=flags, build_directory=t['out'], verbose=False,
          is_python_module=True, **kw)

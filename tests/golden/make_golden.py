@@ -151,7 +151,7 @@ def main():
 
     # ---- (6) full-size digests (arrays too large to commit): base B=1,2 / native / stress
     digests = {}
-    for name, Bs in (('base', (1, 2)), ('native', (1,)), ('stress', (1,))):
+    for name, Bs in (('base', (1, 2, 8)), ('native', (1, 8)), ('stress', (1, 2))):
         shp = SHAPES[name]
         vtf = ref_transformer(mod, shp)
         for Bn in Bs:
@@ -182,6 +182,22 @@ def main():
                 note='ranks_depth/ranks_feat digests are tie-canonicalised (ascending ranks_depth within a voxel)')
     with open(os.path.join(HERE, 'fullsize_digests.json'), 'w') as f:
         json.dump(dict(meta=meta, digests=digests), f, indent=1, sort_keys=True)
+
+    # ---- (6b) occ_pool: the reference's own pure-PyTorch implementation (OCC_Pool.py:39-71), executed here
+    import importlib.util
+    from tests.golden._ref_import import REFERENCE_ROOT
+    op = os.path.join(REFERENCE_ROOT, 'projects', 'CONet', 'mmdet3d_plugin', 'ops', 'occ_pooling', 'OCC_Pool.py')
+    spec = importlib.util.spec_from_file_location('_ref_occ_pool', op)
+    occ = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(occ)
+    go = torch.Generator().manual_seed(11)
+    oB, oD, oH, oW, oC, oN = 2, 4, 24, 20, 8, 6000
+    ocoords = torch.minimum((torch.rand(oN, 4, generator=go) * torch.tensor([oH, oW, oD, oB])).long(),
+                            torch.tensor([oH, oW, oD, oB]) - 1).int()
+    ofeats = torch.randn(oN, oC, generator=go)
+    oout = occ.occ_pool_pure_pytorch(ofeats, ocoords, oB, oD, oH, oW)
+    np.savez_compressed(os.path.join(HERE, 'occ_pool_ref.npz'), feats=ofeats.numpy(), coords=ocoords.numpy(),
+                        out=oout.numpy(), dims=np.array([oB, oD, oH, oW]))
 
     # ---- (7) the reference's known-answer test, as data (bev_pool.py:145-176)
     np.savez(os.path.join(HERE, 'kat_bev_pool_v2.npz'),

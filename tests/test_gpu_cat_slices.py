@@ -71,3 +71,26 @@ def test_slice_leaves_other_channels_untouched_and_handles_unsorted_ranks():
     assert plan.flags() & 1, 'shuffled intervals must be detected as unsorted'
     assert torch.equal(_bits(wide[:, 5:13]), _bits(want))
     assert bool((wide[:, :5] == 7.0).all()) and bool((wide[:, 13:] == 7.0).all())
+
+
+def test_cat_against_the_oracle_directly():
+    """bev_pool_v2_cat against the C restatement of the reference kernels (oracle/kernels.py) itself —
+    not against the repo's own op: every channel slice and both gradients of every frame, bit for bit."""
+    from oracle import kernels as ok
+    chans = (16, 8)
+    frames, (B, Z, Y, X) = _frames('small', 2, len(chans), chans)
+    leaves = [(f[0].clone().requires_grad_(), f[1].clone().requires_grad_()) for f in frames]
+    got = bev_pool_v2_cat([(d, ft) + f[2:] for (d, ft), f in zip(leaves, frames)], (B, Z, Y, X, chans[0]))
+    og = torch.randn(got.shape, generator=torch.Generator().manual_seed(9))
+    got.backward(og.to(DEV))
+    off = 0
+    for (d, ft), f, c in zip(leaves, frames, chans):
+        rd, rf, rb, st, ln = (t.cpu().numpy() for t in f[2:])
+        dn, fn = f[0].cpu().numpy(), f[1].cpu().numpy()
+        want = ok.bev_pool_v2(dn, fn, rd, rf, rb, (B, Z, Y, X, c), st, ln)
+        assert np.array_equal(got[:, off:off + c].detach().cpu().contiguous().numpy().view(np.uint32),
+                              np.ascontiguousarray(want).view(np.uint32)), f'slice [{off},{off + c})'
+        wdg, wfg = ok.bev_pool_v2_backward(np.ascontiguousarray(og[:, off:off + c].numpy()), dn, fn, rd, rf, rb)
+        assert np.array_equal(d.grad.cpu().numpy().view(np.uint32), np.ascontiguousarray(wdg).view(np.uint32))
+        assert np.array_equal(ft.grad.cpu().numpy().view(np.uint32), np.ascontiguousarray(wfg).view(np.uint32))
+        off += c

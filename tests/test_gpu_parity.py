@@ -108,13 +108,13 @@ def test_rank_prepare_fp32_hazard_is_exact_integers(golden_dir):
     assert not np.array_equal(got[0], g['ranks_bev']), 'expected the fp32 reference ranks to be inexact at B=28'
 
 
-@pytest.mark.parametrize('case', ['base_B1', 'base_B2', 'native_B1', 'stress_B1'])
+@pytest.mark.parametrize('case', ['base_B1', 'base_B2', 'base_B8', 'native_B1', 'native_B8', 'stress_B1', 'stress_B2'])
 def test_rank_prepare_fullsize_digests(golden_dir, case):
     """Full BASELINE shapes: sha256 of all five arrays against digests of the reference's own output."""
     with open(os.path.join(golden_dir, 'fullsize_digests.json')) as f:
         dig = json.load(f)['digests'][case]
     name, B = case.split('_B')
-    c = rig_case(name, int(B))
+    c = rig_case(name, int(B), with_ranks=False)
     assert sha(c['coor'].numpy()) == dig['coor'], 'rig/geometry drifted from the golden generation'
     got, _ = _run_rank_prepare(c['coor'].numpy(), c['lb'], c['itv'], c['gs'])
     assert got[0].shape[0] == dig['n_kept'] and got[3].shape[0] == dig['n_intervals']

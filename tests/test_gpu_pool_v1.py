@@ -12,21 +12,7 @@ DEV = 'cuda:0'
 RTOL = ATOL = 1e-5
 
 
-def oracle_v1(feats, coords, B, D, H, W):
-    """numpy: sort by our voxel id (stable), sequential fp32 sum per voxel, (B,C,D,H,W) output."""
-    x, y, z, b = (coords[:, i].astype(np.int64) for i in range(4))
-    key = ((b * D + z) * H + x) * W + y
-    order = np.argsort(key, kind='stable')
-    out = np.zeros((B * D * H * W, feats.shape[1]), np.float32)
-    ks = key[order]
-    starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
-    ends = np.r_[starts[1:], len(ks)]
-    for s, e in zip(starts, ends):
-        acc = np.zeros(feats.shape[1], np.float32)
-        for i in order[s:e]:
-            acc = (acc + feats[i]).astype(np.float32)
-        out[ks[s]] = acc
-    return out.reshape(B, D, H, W, -1).transpose(0, 4, 1, 2, 3)
+from oracle.pool_v1 import pool_v1 as oracle_v1  # noqa: E402  (numpy restatement, pinned by tests/golden/occ_pool_ref.npz)
 
 
 def occ_pool_pure_pytorch(feats, coords, B, D, H, W):
@@ -99,3 +85,36 @@ def test_rank_from_keys_is_the_stable_sort():
     starts = np.flatnonzero(np.r_[True, k[o][1:] != k[o][:-1]])
     assert ni == len(starts) and np.array_equal(st[:ni].cpu().numpy(), starts)
     assert np.array_equal(ln[:ni].cpu().numpy(), np.diff(np.r_[starts, nk]))
+
+
+@pytest.mark.parametrize('n,B,D,H,W,C,clustered', [(120000, 4, 1, 180, 180, 80, False), (60000, 2, 8, 64, 64, 32, True)])
+def test_bev_pool_v1_vs_unmodified_bevfusion_extension(n, B, D, H, W, C, clustered):
+    """f-4 parity pin: projects/BEVFusion/bevfusion/ops/bev_pool/src/* compiled unmodified by
+    oracle/build_ref.py --which v1, wrapped with the reference's own op sequence (bev_pool.py:37-99, restated in
+    oracle/ref_ext.py).  Forward and x_grad bit-identical (same sequential sum in stable-sorted order) at a
+    BEVFusion-sized grid (180 x 180 x 1, C = 80) and a clustered 3-D case."""
+    from oracle import ref_ext
+    if not ref_ext.available('v1'):
+        pytest.skip('oracle/_ref_v1 not built (reference tree absent at build time)')
+    feats, coords = _case(n, B, D, H, W, C, 5, clustered)
+    fa = feats.to(DEV).requires_grad_()
+    fb = feats.to(DEV).requires_grad_()
+    cd = coords.to(DEV)
+    got = bev_pool(fa, cd, B, D, H, W)
+    want = ref_ext.bev_pool_v1(fb, cd, B, D, H, W)
+    assert got.shape == want.shape == (B, C, D, H, W)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32)), 'forward differs from bev_pool_ext'
+    og = torch.randn(got.shape, generator=torch.Generator().manual_seed(6)).to(DEV)
+    got.backward(og)
+    want.backward(og)
+    assert torch.equal(fa.grad.view(torch.int32), fb.grad.view(torch.int32)), 'x_grad differs from bev_pool_ext'
+
+
+def test_occ_pool_vs_reference_generated_golden(golden_dir):
+    """tests/golden/occ_pool_ref.npz was produced by EXECUTING the reference's own occ_pool_pure_pytorch
+    (projects/CONet/mmdet3d_plugin/ops/occ_pooling/OCC_Pool.py:39-71) on CPU (tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(golden_dir, 'occ_pool_ref.npz'))
+    B, D, H, W = (int(v) for v in g['dims'])
+    got = occ_pool(torch.from_numpy(g['feats']).to(DEV), torch.from_numpy(g['coords']).to(DEV), B, D, H, W)
+    torch.testing.assert_close(got.cpu(), torch.from_numpy(g['out']), rtol=RTOL, atol=ATOL)

@@ -134,3 +134,13 @@ def test_oracle_vs_reference_live():
     crb, crd, crf = canon(ref[0], ref[1], ref[2])
     for a, b in zip(got, (crb, crd, crf, ref[3], ref[4])):
         np.testing.assert_array_equal(a, b)
+
+
+def test_pool_v1_oracle_vs_reference_generated_golden(golden_dir):
+    """The sibling-op oracle (oracle/pool_v1.py) against the output of the reference's own occ_pool_pure_pytorch
+    (OCC_Pool.py:39-71, executed by tests/golden/make_golden.py): rtol=atol=1e-5 (index_add_ order is not defined)."""
+    from oracle.pool_v1 import pool_v1
+    g = np.load(os.path.join(golden_dir, 'occ_pool_ref.npz'))
+    B, D, H, W = (int(v) for v in g['dims'])
+    got = pool_v1(g['feats'], g['coords'], B, D, H, W)
+    np.testing.assert_allclose(got, g['out'], rtol=1e-5, atol=1e-5)
