@@ -17,7 +17,10 @@
 //   * single-warp CTAs, no __syncthreads in the main kernel: up to 32 independent warps per SM walk the
 //     3-round-trip dependency chain of their sub-tiles; the few very dense sub-tiles (listed by the plan) are
 //     split over eight "front" CTAs each, which start first.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace fo {
 
@@ -44,6 +47,7 @@ struct FwdArgs {
     int32_t front_y;                // grid rows (blockIdx.y) reserved for front CTAs; 0: everything inline
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
+    int32_t store_evict_first;      // bulk-store write-out: L2 evict-first hint (sparse frusta; see forward_impl)
 };
 
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
@@ -91,7 +95,7 @@ constexpr int kFrontSlots  = FO_FRONT_SLOTS;  // front CTAs per launch (they loo
 //   * record words / depth values are broadcast through shared memory (LDS.128, no shuffles), feature rows
 //     are fetched in groups of U with the NEXT group already in flight (2*U rows in flight per lane), and the
 //     next 32 records are fetched while a batch is processed.
-template <int NACC, bool EXACT, int U = (NACC <= 2 ? FO_FWD_U : 4)>   // U = feature rows per group
+template <int NACC, bool EXACT, bool XSWZ = false, int U = (NACC <= 2 ? FO_FWD_U : 4)>   // U = feature rows per group
 __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, const int lane, const int p_lo,
                                               const int p_hi, const int bV, int *rx, float *rdv,
                                               const unsigned lane_row, const unsigned lane_rot) {
@@ -111,7 +115,8 @@ __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, con
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
     int cur_v = -1;
     auto flush = [&]() {
-        const unsigned off = (((unsigned)cur_v << 2) + lane_rot) & 127u;
+        // rows rotated by (c & 7) 16-byte chunks, or (XSWZ) the TMA engine's 128-byte swizzle: chunk ^ (c & 7)
+        const unsigned off = XSWZ ? ((((unsigned)cur_v << 2) ^ lane_rot) & 127u) : ((((unsigned)cur_v << 2) + lane_rot) & 127u);
 #pragma unroll
         for (int k = 0; k < NACC; ++k)
             if (EXACT || lane + 32 * k < C) sts_f32(lane_row + off + 4096u * k, acc[k]);
@@ -199,9 +204,12 @@ __device__ __forceinline__ void reduce_points(const FwdArgs &a, const int C, con
 // point counts) of a listed sub-tile, reduces it into its own stage and writes exactly the voxel columns from its
 // first interval's voxel up to the next group's — so the groups tile the sub-tile and every element is still
 // written once.  They start first and overlap with the bulk of the grid; regular CTAs skip listed sub-tiles.
-template <int NACC, bool EXACT, int LAYOUT>
-__global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a) {
-    extern __shared__ __align__(16) float smem[];        // stage [C][32]
+// TMAST: the staged block (128-byte-swizzled rows) leaves through ONE cp.async.bulk.tensor store issued by lane 0
+// instead of 8 LDS.128 + 8 STG.128 per lane (measured in profiles/r02_summary.md).
+template <int NACC, bool EXACT, int LAYOUT, bool TMAST>
+__global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs a, const __grid_constant__ CUtensorMap tm) {
+    extern __shared__ __align__(1024) float smem_raw[];  // stage [C][32]
+    float *smem = TMAST ? reinterpret_cast<float *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023) : smem_raw;
     __shared__ __align__(16) int s_rx[32 + 8];           // (feature row << 5 | voxel slot) per point
     __shared__ __align__(16) float s_rd[32 + 8];         // depth value per point
 
@@ -287,8 +295,20 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
     } else {
         for (int e = lane; e < C * (kSub / 4); e += 32) sts_zero4(sbase + 16u * e);
     }
-    reduce_points<NACC, EXACT>(a, C, lane, pa, pb, bV, s_rx, s_rd, sbase + ((unsigned)lane << 7),
-                               ((unsigned)lane & 7u) << 4);
+    reduce_points<NACC, EXACT, TMAST>(a, C, lane, pa, pb, bV, s_rx, s_rd, sbase + ((unsigned)lane << 7),
+                                      ((unsigned)lane & 7u) << 4);
+    if (TMAST) {
+        fence_proxy_async_smem();                         // the flushes (generic proxy) -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+            // C rows x 128 bytes; voxels beyond V are not written
+            if (a.store_evict_first) tma_store_3d_hint(&tm, v0, 0, b, sbase, l2_policy_evict_first());
+            else tma_store_3d(&tm, v0, 0, b, sbase);
+            bulk_commit();
+            bulk_wait_read0();                            // the stage must outlive the store's reads
+        }
+        return;
+    }
     __syncwarp();
 
     if (LAYOUT == FO_LAYOUT_BCZYX) {
@@ -397,34 +417,43 @@ using namespace fo;
 
 namespace {
 template <int NACC, bool EXACT, int LAYOUT>
-int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
-    auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT>;
+int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream, const CUtensorMap *tm) {
+    if (tm != nullptr && LAYOUT == FO_LAYOUT_BCZYX) {
+        auto kern = fwd_dense_kernel<NACC, EXACT, FO_LAYOUT_BCZYX, true>;
+        const size_t sm2 = smem + 1024;
+        if (sm2 > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        kern<<<dim3(a.B, n_ctas + a.front_y), 32, sm2, stream>>>(a, *tm);
+        FO_LAUNCH_CHECK("fwd_dense_kernel<tma>");
+        return FO_OK;
+    }
+    auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT, false>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(a.B, n_ctas + a.front_y), 32, smem, stream>>>(a);
+    CUtensorMap dummy{};
+    kern<<<dim3(a.B, n_ctas + a.front_y), 32, smem, stream>>>(a, dummy);
     FO_LAUNCH_CHECK("fwd_dense_kernel");
     return FO_OK;
 }
 template <int LAYOUT>
-int launch_dense_any(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream) {
+int launch_dense_any(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream, const CUtensorMap *tm) {
     const int nacc = (a.C + 31) / 32;
     if (a.C % 32 == 0) {
         switch (nacc) {
-            case 1: return launch_dense<1, true, LAYOUT>(a, n_ctas, smem, stream);
-            case 2: return launch_dense<2, true, LAYOUT>(a, n_ctas, smem, stream);
-            case 3: return launch_dense<3, true, LAYOUT>(a, n_ctas, smem, stream);
-            case 4: return launch_dense<4, true, LAYOUT>(a, n_ctas, smem, stream);
+            case 1: return launch_dense<1, true, LAYOUT>(a, n_ctas, smem, stream, tm);
+            case 2: return launch_dense<2, true, LAYOUT>(a, n_ctas, smem, stream, tm);
+            case 3: return launch_dense<3, true, LAYOUT>(a, n_ctas, smem, stream, tm);
+            case 4: return launch_dense<4, true, LAYOUT>(a, n_ctas, smem, stream, tm);
             default: break;
         }
     }
     switch (nacc) {
-        case 1: return launch_dense<1, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 2: return launch_dense<2, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 3: return launch_dense<3, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 4: return launch_dense<4, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 5: return launch_dense<5, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 6: return launch_dense<6, false, LAYOUT>(a, n_ctas, smem, stream);
-        case 7: return launch_dense<7, false, LAYOUT>(a, n_ctas, smem, stream);
-        default: return launch_dense<8, false, LAYOUT>(a, n_ctas, smem, stream);
+        case 1: return launch_dense<1, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 2: return launch_dense<2, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 3: return launch_dense<3, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 4: return launch_dense<4, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 5: return launch_dense<5, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 6: return launch_dense<6, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        case 7: return launch_dense<7, false, LAYOUT>(a, n_ctas, smem, stream, tm);
+        default: return launch_dense<8, false, LAYOUT>(a, n_ctas, smem, stream, tm);
     }
 }
 }  // namespace
@@ -467,8 +496,22 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     const int n_ctas = sps;                                           // per sample (grid.y)
     const bool dense_ok = smem <= 200 * 1024 && c <= 256 && n_ctas + a.front_y <= 65535 && B <= 65535;
     if (dense_ok) {
-        int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream)
-                                                 : launch_dense_any<FO_LAYOUT_BZYXC>(a, n_ctas, smem, stream);
+        // Write-out through ONE bulk tensor store per sub-tile (FO_FWD_TMA=0 selects the LDS.128 + STG.128 path for
+        // A/B runs).  Measured on a B200 (profiles/r02_summary.md): with the L2 evict-first hint 146.7 -> 141.8 us at
+        // the headline shape batch 8 and 25.1 -> 21.0 us at batch 1, but 276 -> 282 us at 512x1408 (four times the
+        // points per voxel: the kernel then lives on L2-resident index / feature reads); without the hint 272 -> 267 us
+        // there and 146 -> 156 us at the headline shape.  Hence the hint only for sparse frusta.
+        CUtensorMap tm;
+        const CUtensorMap *tmp = nullptr;
+        const char *te = getenv("FO_FWD_TMA");
+        const int use_tma = (te && *te) ? atoi(te) : 1;
+        a.store_evict_first = (n_points < (int64_t)B * n_vox) ? 1 : 0;   // fewer points than voxels (capacity or live count)
+        if (use_tma >= 1 && out_layout == FO_LAYOUT_BCZYX && tmap_ok(a.out, n_vox, c, c_total)) {
+            if (int rc2 = make_voxel_tmap(&tm, a.out, n_vox, c, c_total, B)) return rc2;
+            tmp = &tm;
+        }
+        int rc = (out_layout == FO_LAYOUT_BCZYX) ? launch_dense_any<FO_LAYOUT_BCZYX>(a, n_ctas, smem, stream, tmp)
+                                                 : launch_dense_any<FO_LAYOUT_BZYXC>(a, n_ctas, smem, stream, tmp);
         if (rc) return rc;
     }
     // order-agnostic path, guarded by the plan's flag on the device (no host sync); unconditional when
@@ -528,5 +571,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
     a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
     a.sub_iv = nullptr; a.iv_vox = nullptr; a.heavy_list = nullptr; a.n_heavy = nullptr; a.front_y = 0;
+    a.store_evict_first = 0;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

@@ -101,6 +101,17 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, int x, int y
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(tm), "r"(x), "r"(y), "r"(z), "r"(src) : "memory");
 }
+// same with an L2 eviction-priority hint (the streaming stores of the voxel tensor want evict-first)
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *tm, int x, int y, int z, unsigned src,
+                                                  unsigned long long policy) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                 ::"l"(tm), "r"(x), "r"(y), "r"(z), "r"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the bulk stores of this thread have finished READING shared memory (the stage may be reused / the CTA may exit)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
