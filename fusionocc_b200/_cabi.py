@@ -49,6 +49,10 @@ SIGNATURES = {
     'fo_bev_pool_v2_backward': (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int64,
                                         c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_void_p, c_size_t, c_void_p, c_size_t]),
+    'fo_bev_pool_v2_backward_with_plan': (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
+                                                  c_void_p, c_int64, c_int32, c_int64, c_int64, c_int64, c_int32,
+                                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
+                                                  c_size_t]),
     'fo_rank_prepare_scratch_bytes': (c_size_t, [c_int64, c_int64]),
     'fo_rank_prepare': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, _f3, _f3, c_int32,
                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -92,8 +92,7 @@ class VoxelPoolPlan:
         """The inverse interval ordering.  It bakes ``ranks_depth`` in, so it is rebuilt whenever the
         ``ranks_depth`` / ``ranks_feat`` the caller passes (``sig``: identity, version counter, address) or the
         depth / feature sizes differ from the ones it was built for."""
-        structured = (self.structured_hw > 0 and self.n_depth == n_depth and n_feat_rows % self.structured_hw == 0
-                      and n_depth % n_feat_rows == 0 and n_depth // n_feat_rows <= 256)
+        structured = self._structured(n_depth, n_feat_rows)
         key = (n_depth, n_feat_rows) if structured else (n_depth, n_feat_rows, sig)
         if self.bwd is None or self.bwd_key != key:
             lib = _cabi.load()
@@ -109,6 +108,14 @@ class VoxelPoolPlan:
                     self.n_vox, _p(buf), nbytes), 'fo_bwd_plan_build')
             self.bwd, self.bwd_key, self.bwd_rows = buf, key, n_feat_rows
         return self.bwd
+
+    def _structured(self, n_depth: int, n_feat_rows: int) -> bool:
+        return (self.structured_hw > 0 and self.n_depth == n_depth and n_feat_rows % self.structured_hw == 0
+                and n_depth % n_feat_rows == 0 and n_depth // n_feat_rows <= 256)
+
+    def needs_structured_bwd(self, n_depth: int, n_feat_rows: int) -> bool:
+        """True when the backward plan can be built per pixel from the forward plan and is not there yet."""
+        return self._structured(n_depth, n_feat_rows) and (self.bwd is None or self.bwd_key != (n_depth, n_feat_rows))
 
     def bwd_scratch(self, nbytes: int, device) -> torch.Tensor:
         """Gather scratch of the backward, kept with the plan (it is sized by the plan's interval capacity, so
@@ -214,12 +221,26 @@ def native_backward(out_grad, og_layout, depth, feat, ranks_depth, ranks_feat, b
     B, Z, Y, X, C = (int(s) for s in bev_feat_shape)
     dev = depth.device
     n_feat_rows = feat.numel() // C
-    bwd = plan.ensure_bwd(ranks_depth, ranks_feat, depth.numel(), n_feat_rows,
-                          rank_sig if rank_sig is not None else _sig(ranks_depth, ranks_feat))
     depth_grad = torch.empty_like(depth)
     feat_grad = torch.empty_like(feat)
     sbytes = lib.fo_bwd_scratch_bytes(plan.n_intervals, C, og_layout)
     scratch = plan.bwd_scratch(sbytes, dev)
+    n_depth = depth.numel()
+    if c_total is None and plan.needs_structured_bwd(n_depth, n_feat_rows):
+        # first backward on a plan from the rank precompute: the inverse ordering is built INSIDE this call
+        # (riding along the gather kernel) and kept with the plan
+        nbytes = lib.fo_bwd_plan_bytes(n_depth, n_feat_rows)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.fo_bev_pool_v2_backward_with_plan(
+                _stream(dev), C, _p(out_grad), og_layout, _p(depth), _p(feat), plan.n_points, plan.n_points_dev_ptr(),
+                plan.n_intervals, B, Z * Y * X, n_depth, n_feat_rows, plan.structured_hw, _p(depth_grad),
+                _p(feat_grad), _p(plan.fwd), plan.fwd.numel(), _p(buf), nbytes, _p(scratch), sbytes),
+                'fo_bev_pool_v2_backward_with_plan')
+        plan.bwd, plan.bwd_key, plan.bwd_rows = buf, (n_depth, n_feat_rows), n_feat_rows
+        return depth_grad, feat_grad
+    bwd = plan.ensure_bwd(ranks_depth, ranks_feat, n_depth, n_feat_rows,
+                          rank_sig if rank_sig is not None else _sig(ranks_depth, ranks_feat))
     with torch.cuda.device(dev):
         if c_total is None:
             _cabi.check(lib.fo_bev_pool_v2_backward(

@@ -15,6 +15,7 @@
 //            the reference's exact orders, no atomics, every output written once.
 #include <stdlib.h>
 
+#include "bwd_plan.cuh"
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -524,6 +525,61 @@ __global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const
         gather_emit<NACC, EXACT>(a, stage, bar, 0, lane, t);
 }
 
+// The gather with the BACKWARD PLAN riding along: one launch, two kinds of CTAs.  Every k-th CTA of the grid builds the
+// inverse interval ordering of 16 image pixels (plan_pixel_bitonic, bwd_plan.cuh: comparison networks in registers,
+// issue-bound); the others are gather CTAs (DRAM-bound, 32 % of the issue slots busy).  The plan depends only on the
+// forward plan, so there is no ordering between the two kinds; interleaving them in block order puts about one plan
+// CTA next to four gather CTAs on every SM for the whole launch.  (As separate launches on two streams the block
+// scheduler ran them back to back; as a ninth warp inside every gather CTA the plan warp outlived its CTA's gather
+// warps several times over and held their slots — profiles/r02_summary.md.)
+struct PlanRideArgs {
+    const int32_t *pt2vox, *vox2iv;
+    int32_t D, HW, n_rows;
+    int32_t n_plan_ctas, n_gather_ctas, gu;   // gu = gather CTAs per sample
+    BwdPlanHeader *hdr;
+    int32_t *ent_p, *ent_iv, *starts, *lengths, *ids;
+    const int32_t *n_points_dev;
+};
+constexpr int kPlanPixPerWarp = 2;
+
+template <int NACC, bool EXACT, int R>
+__global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, PlanRideArgs p,
+                                                                 const __grid_constant__ CUtensorMap tm) {
+    extern __shared__ __align__(1024) unsigned char gsm[];
+    __shared__ __align__(8) unsigned long long s_bar[8];
+    __shared__ int s_cmp[8][32 * R];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long T = (long long)p.n_plan_ctas + p.n_gather_ctas;
+    const int bid = blockIdx.x;
+    const int plans_before = (int)(((long long)bid * p.n_plan_ctas) / T);
+    const bool is_plan = (int)(((long long)(bid + 1) * p.n_plan_ctas) / T) > plans_before;
+    if (is_plan) {
+        if (plans_before == 0 && threadIdx.x == 0) {
+            p.hdr->n_bwd_intervals = p.n_rows;
+            p.hdr->n_points = p.n_points_dev ? *p.n_points_dev : 0;
+            p.hdr->structured = 1;
+        }
+        const int q0 = (plans_before * 8 + warp) * kPlanPixPerWarp;
+#pragma unroll 1
+        for (int q = q0; q < min(p.n_rows, q0 + kPlanPixPerWarp); ++q)
+            plan_pixel_bitonic<R>(p.pt2vox, p.vox2iv, p.D, p.HW, q, s_cmp[warp], lane, p.ent_p, p.ent_iv, p.starts,
+                                  p.lengths, p.ids);
+        return;
+    }
+    const int gi = bid - plans_before;
+    const int b = gi / p.gu, blk = gi - b * p.gu;
+    const int C = EXACT ? 32 * NACC : a.C;
+    const unsigned stage_bytes = ((unsigned)C * 128u + 1023u) & ~1023u;
+    unsigned char *base = (unsigned char *)(((uintptr_t)gsm + 1023) & ~(uintptr_t)1023);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    float *stage = reinterpret_cast<float *>(base + warp * stage_bytes);
+    GatherTile t;
+    if (gather_issue<NACC, EXACT>(a, &tm, stage, bar, b, blk * 8 + warp, lane, t))
+        gather_emit<NACC, EXACT>(a, stage, bar, 0, lane, t);
+}
+
 // Order-agnostic gather for plans whose interval list is not canonical (kFlagUnsorted): one warp per interval,
 // G[k, :] = out_grad[b, :, voxel(k)]; intervals without a valid voxel get a zero row (never read: their points
 // carry row -1).
@@ -675,6 +731,12 @@ int bwd_impl_choice() {
     return (e && *e) ? atoi(e) : 1;
 }
 
+// FO_BWD_RIDE=0 (A/B): build a requested plan as its own launch instead of inside the gather kernel
+bool bwd_ride_choice() {
+    const char *e = getenv("FO_BWD_RIDE");
+    return !(e && *e) || atoi(e) != 0;
+}
+
 int launch_pixel2(const PixelArgs &pa, cudaStream_t stream) {
     const int64_t pixels = pa.n_bwd;
     if (pixels <= 0) return FO_OK;
@@ -701,11 +763,15 @@ int launch_pixel2(const PixelArgs &pa, cudaStream_t stream) {
 }  // namespace
 
 namespace {
+struct PlanRequest {          // build the (structured) backward plan inside this call
+    const int32_t *n_points_dev;
+    int32_t hw;
+};
 int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t og_layout, int32_t c_total,
                   int32_t c_offset, const float *depth, const float *feat, int64_t n_points, int64_t n_intervals,
                   int32_t B, int64_t n_vox, int64_t n_depth, int64_t n_feat_rows, float *depth_grad,
                   float *feat_grad, const void *fwd_plan, size_t fwd_plan_bytes, const void *bwd_plan,
-                  size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+                  size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes, const PlanRequest *req = nullptr) {
     FO_CHECK_ARG(c >= 1 && c_offset >= 0 && c_total >= c && c_offset + c <= c_total,
                  "channel slice [%d, %d) does not fit %d channels", c_offset, c_offset + c, c_total);
     FO_CHECK_ARG(c >= 1 && B >= 1 && n_vox >= 1, "c, B and voxels per sample must be positive");
@@ -715,7 +781,15 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
     FO_CHECK_ARG(n_points < INT_MAX && (int64_t)B * n_vox < INT_MAX && n_depth < INT_MAX, "sizes exceed int32 ranks");
     FO_CUDA(cudaMemsetAsync(depth_grad, 0, (size_t)n_depth * 4, stream));
     FO_CUDA(cudaMemsetAsync(feat_grad, 0, (size_t)n_feat_rows * c * 4, stream));
-    if (n_points == 0 || n_intervals == 0) return FO_OK;
+    // a requested plan rides along the gather when it can (below); otherwise it is built first, as a separate launch
+    bool plan_pending = req != nullptr;
+    auto build_plan_now = [&]() -> int {
+        plan_pending = false;
+        return fo_bwd_plan_build((fo_stream_t)stream, nullptr, nullptr, n_points, req->n_points_dev, n_depth, n_feat_rows,
+                                 req->hw, FO_BWD_PLAN_STRUCTURED, fwd_plan, fwd_plan_bytes, B, n_vox,
+                                 const_cast<void *>(bwd_plan), bwd_plan_bytes);
+    };
+    if (n_points == 0 || n_intervals == 0) return plan_pending ? build_plan_now() : FO_OK;
     FO_CHECK_ARG(out_grad && depth && feat, "NULL input array");
     FO_CHECK_ARG(bwd_plan != nullptr, "backward plan is required");
     FwdPlanView pv; int64_t n_subs; int sps;
@@ -751,8 +825,11 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         if (c > 256 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "channel or batch count too large for the gather kernel");
         // plans built from caller-supplied intervals may be flagged non-canonical on the device: the per-interval
         // gather fills G then (it exits at once otherwise), and the sub-tile gathers exit
-        bwd_gather_flagged_kernel<<<grid_for(n_intervals * 32, 256, 8), 256, 0, stream>>>(ga, n_intervals);
-        FO_LAUNCH_CHECK("bwd_gather_flagged_kernel");
+        // (a plan request means the forward plan came from the rank precompute: always canonical, nothing to guard)
+        if (req == nullptr) {
+            bwd_gather_flagged_kernel<<<grid_for(n_intervals * 32, 256, 8), 256, 0, stream>>>(ga, n_intervals);
+            FO_LAUNCH_CHECK("bwd_gather_flagged_kernel");
+        }
         const bool tma = v2_ok && n_intervals * c < INT_MAX && tmap_ok(ga.og, n_vox, c, c_total);
         if (tma) {
             CUtensorMap tm;
@@ -763,6 +840,43 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
             const size_t g_smem = 8 * stage_bytes + 1024;
             const int gu = (sps + 7) / 8;
             if (g_smem <= 200 * 1024 && gu <= 65535) {
+                const int D = (req && n_feat_rows > 0) ? (int)(n_depth / n_feat_rows) : 0;
+                const bool ride = plan_pending && D >= 1 && D <= 128 && (int64_t)B * n_vox < (1 << 24) && req->hw >= 1 &&
+                                  n_feat_rows % req->hw == 0 && n_depth == n_feat_rows * D && n_depth <= pv.p_cap &&
+                                  bv.cap >= n_depth && (int64_t)gu * B + n_feat_rows / 16 + 1 < INT_MAX &&
+                                  g_smem <= 48 * 1024 &&      // wide channel counts leave two gather CTAs per SM: no room to share
+                                  bwd_ride_choice();
+                if (ride) {
+                    PlanRideArgs pr;
+                    pr.pt2vox = pv.pt2vox; pr.vox2iv = pv.vox2iv; pr.D = D; pr.HW = req->hw; pr.n_rows = (int)n_feat_rows;
+                    pr.gu = gu; pr.n_gather_ctas = gu * B;
+                    pr.n_plan_ctas = (int)((n_feat_rows + 8 * kPlanPixPerWarp - 1) / (8 * kPlanPixPerWarp));
+                    pr.hdr = bv.hdr; pr.ent_p = bv.ent_p; pr.ent_iv = bv.ent_iv; pr.starts = bv.starts;
+                    pr.lengths = bv.lengths; pr.ids = bv.ids; pr.n_points_dev = req->n_points_dev;
+                    const int R = D <= 32 ? 1 : (D <= 64 ? 2 : 4);
+#define FO_GRIDE(NA, EX, RR)                                                                                          \
+    do {                                                                                                              \
+        if (g_smem > 48 * 1024)                                                                                       \
+            FO_CUDA(cudaFuncSetAttribute(bwd_gather_plan_kernel<NA, EX, RR>,                                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));                  \
+        bwd_gather_plan_kernel<NA, EX, RR><<<(unsigned)(pr.n_gather_ctas + pr.n_plan_ctas), 256, g_smem, stream>>>(ga, pr, tm); \
+    } while (0)
+#define FO_GRIDE_R(NA, EX)                                                                                            \
+    do {                                                                                                              \
+        if (R == 1) FO_GRIDE(NA, EX, 1); else if (R == 2) FO_GRIDE(NA, EX, 2); else FO_GRIDE(NA, EX, 4);              \
+    } while (0)
+                    if (nacc == 1) { if (exact) FO_GRIDE_R(1, true); else FO_GRIDE_R(1, false); }
+                    else if (nacc == 2) { if (exact) FO_GRIDE_R(2, true); else FO_GRIDE_R(2, false); }
+                    else if (nacc == 3) { if (exact) FO_GRIDE_R(3, true); else FO_GRIDE_R(3, false); }
+                    else { if (exact) FO_GRIDE_R(4, true); else FO_GRIDE_R(4, false); }
+#undef FO_GRIDE_R
+#undef FO_GRIDE
+                    FO_LAUNCH_CHECK("bwd_gather_plan_kernel");
+                    plan_pending = false;
+                    return launch_pixel2(pa, stream);
+                }
+                if (plan_pending)
+                    if (int rc = build_plan_now()) return rc;
 #define FO_GTMA(NA, EX)                                                                                            \
     do {                                                                                                           \
         if (g_smem > 48 * 1024)                                                                                    \
@@ -780,6 +894,8 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
             }
         }
         // round-1 sub-tile gather (LDG path): any V, any C <= 256
+        if (plan_pending)
+            if (int rc = build_plan_now()) return rc;
         const size_t smem = (size_t)kWarpsPerCta * kSub * c * sizeof(float);
         if (smem > 200 * 1024) return set_error(FO_ERR_UNSUPPORTED, "C=%d too large for the gather tile", c);
         const int n_ctas = (sps + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -814,6 +930,8 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
 #undef FO_GATHER
         FO_LAUNCH_CHECK("bwd_gather_kernel");
     } else {
+        if (plan_pending)
+            if (int rc = build_plan_now()) return rc;
         pa.G = out_grad + c_offset; pa.row_map = pv.iv_vox; pa.n_rows_G = (int64_t)B * n_vox; pa.g_rowstride = c_total;
     }
     if (v2_ok && (((uintptr_t)pa.G & 15) == 0) && (pa.g_rowstride % 4 == 0) && pa.n_rows_G * pa.g_rowstride < INT_MAX)
@@ -857,4 +975,23 @@ extern "C" void fo_compat_bev_pool_v2_grad(int c, int n_intervals, const float *
     compat_grad_kernel<<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(
         c, n_intervals, out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths,
         depth_grad, feat_grad);
+}
+
+// Backward INCLUDING the construction of the (structured) backward plan: what fo_bwd_plan_build(FO_BWD_PLAN_STRUCTURED)
+// followed by fo_bev_pool_v2_backward does, with the plan built by extra warps of the gather kernel whenever the shape
+// allows it (contiguous (B,C,Z,Y,X) out_grad, D <= 128, B*Z*Y*X < 2^24), as a separate launch otherwise.
+extern "C" int fo_bev_pool_v2_backward_with_plan(fo_stream_t stream_, int32_t c, const float *out_grad,
+                                                 int32_t og_layout, const float *depth, const float *feat,
+                                                 int64_t n_points, const int32_t *n_points_dev, int64_t n_intervals,
+                                                 int32_t B, int64_t n_vox, int64_t n_depth, int64_t n_feat_rows,
+                                                 int32_t hw_size, float *depth_grad, float *feat_grad,
+                                                 const void *fwd_plan, size_t fwd_plan_bytes, void *bwd_plan,
+                                                 size_t bwd_plan_bytes, void *scratch, size_t scratch_bytes) {
+    FO_CHECK_ARG(bwd_plan != nullptr && ((uintptr_t)bwd_plan & 255) == 0, "backward plan must be non-NULL, 256-byte aligned");
+    FO_CHECK_ARG(hw_size >= 1 && n_feat_rows >= 1 && n_feat_rows % hw_size == 0 && n_depth % n_feat_rows == 0,
+                 "structured plan needs n_depth = n_feat_rows * D and n_feat_rows = B*N*hw_size");
+    PlanRequest req{n_points_dev, hw_size};
+    return backward_impl((cudaStream_t)stream_, c, out_grad, og_layout, c, 0, depth, feat, n_points, n_intervals, B,
+                         n_vox, n_depth, n_feat_rows, depth_grad, feat_grad, fwd_plan, fwd_plan_bytes, bwd_plan,
+                         bwd_plan_bytes, scratch, scratch_bytes, &req);
 }

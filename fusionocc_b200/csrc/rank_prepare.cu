@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "bucket_sort.cuh"
+#include "bwd_plan.cuh"
 
 namespace fo {
 
@@ -306,28 +307,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
     }
 }
 
-// Same job with a bitonic network over packed 32-bit keys (voxel id << 7 | depth bin).  Needs B*Z*Y*X < 2^24
-// and D <= 128.  Only ~57 % of a pixel's depth bins land inside the grid, so the valid keys are first COMPACTED
-// (ballot + popc through a per-warp shared-memory row) and the network is sized to the live count: 32 / 64 / 128
-// elements = 15 / 21x2 / 28x4 compare-exchange steps (the kernel is issue-bound: 34 -> 2x us at the headline shape).
-template <int RS>
-__device__ __forceinline__ void plan_sort_emit(const int *cmp, const int n, const int lane, const int ebase,
-                                               const int pbase, const int HW, const int32_t *__restrict__ vox2iv,
-                                               int32_t *ent_p, int32_t *ent_iv) {
-    int key[RS];
-#pragma unroll
-    for (int r = 0; r < RS; ++r) key[r] = (32 * r + lane < n) ? cmp[32 * r + lane] : INT_MAX;
-    bitonic_sort_regs<RS>(key, lane);
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-        const int e = 32 * r + lane;
-        if (e < n) {
-            ent_p[ebase + e] = pbase + (key[r] & 127) * HW;
-            ent_iv[ebase + e] = __ldg(vox2iv + (key[r] >> 7));
-        }
-    }
-}
-
+// Same job with a bitonic network over packed 32-bit keys (bwd_plan.cuh: plan_pixel_bitonic).
 template <int R>   // R in {1, 2, 4}: 32 * R >= D
 __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     const int32_t *__restrict__ pt2vox, const int32_t *__restrict__ vox2iv, int D, int HW, int n_rows,
@@ -338,41 +318,13 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     int *cmp = s_cmp[threadIdx.x >> 5];
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const unsigned lt = (1u << lane) - 1u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
         hdr->structured = 1;
     }
-    for (int q = warp0; q < n_rows; q += nwarps) {
-        const int bn = q / HW, hw = q - bn * HW;
-        const int pbase = bn * D * HW + hw;
-        int key[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int d = lane + 32 * r;
-            key[r] = -1;
-            if (d < D) {
-                const int v = __ldg(pt2vox + pbase + d * HW);
-                if (v >= 0) key[r] = (v << 7) | d;
-            }
-        }
-        int n = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const unsigned m = __ballot_sync(0xffffffffu, key[r] >= 0);
-            if (key[r] >= 0) cmp[n + __popc(m & lt)] = key[r];
-            n += __popc(m);
-        }
-        __syncwarp();
-        if (n > 0) {
-            if (n <= 32) plan_sort_emit<1>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
-            else if (R >= 2 && n <= 64) plan_sort_emit<(R >= 2 ? 2 : 1)>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
-            else plan_sort_emit<R>(cmp, n, lane, q * D, pbase, HW, vox2iv, ent_p, ent_iv);
-        }
-        if (lane == 0) { starts[q] = q * D; lengths[q] = n; ids[q] = q; }
-        __syncwarp();                                    // the compaction row is reused by the next pixel
-    }
+    for (int q = warp0; q < n_rows; q += nwarps)
+        plan_pixel_bitonic<R>(pt2vox, vox2iv, D, HW, q, cmp, lane, ent_p, ent_iv, starts, lengths, ids);
 }
 
 // Generic build, last step: sorted forward positions -> (depth index, forward interval) entries.

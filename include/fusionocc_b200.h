@@ -177,6 +177,23 @@ int fo_bev_pool_v2_backward(fo_stream_t stream, int32_t c,
                             const void *bwd_plan, size_t bwd_plan_bytes,
                             void *scratch, size_t scratch_bytes);
 
+/* Backward INCLUDING the construction of the structured backward plan (what fo_bwd_plan_build with
+ * FO_BWD_PLAN_STRUCTURED followed by fo_bev_pool_v2_backward does; `bwd_plan` is written by this call and can be
+ * passed to later fo_bev_pool_v2_backward calls while the rank arrays are unchanged).  When out_grad is contiguous
+ * (B,C,Z,Y,X), D <= 128 and B*Z*Y*X < 2^24 the plan is built by extra warps of the gather kernel — the gather is
+ * DRAM-bound, the plan issue-bound, one kernel makes them share every SM — otherwise by a launch of its own.
+ * Requires a forward plan produced by fo_rank_prepare[_calib].  n_points_dev: the live point count (counts_dev). */
+int fo_bev_pool_v2_backward_with_plan(fo_stream_t stream, int32_t c,
+                                      const float *out_grad, int32_t og_layout,
+                                      const float *depth, const float *feat,
+                                      int64_t n_points, const int32_t *n_points_dev, int64_t n_intervals,
+                                      int32_t B, int64_t n_voxels_per_sample,
+                                      int64_t n_depth, int64_t n_feat_rows, int32_t hw_size,
+                                      float *depth_grad, float *feat_grad,
+                                      const void *fwd_plan, size_t fwd_plan_bytes,
+                                      void *bwd_plan, size_t bwd_plan_bytes,
+                                      void *scratch, size_t scratch_bytes);
+
 /* Same, reading the gradient of a channel slice [c_offset, c_offset + c) out of the gradient of the wide
  * tensor (`out_grad` = base of the (B,c_total,Z,Y,X) / (B,Z,Y,X,c_total) gradient): no slicing copy. */
 int fo_bev_pool_v2_backward_slice(fo_stream_t stream, int32_t c,

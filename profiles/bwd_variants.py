@@ -52,7 +52,27 @@ def main():
         res[f'impl{impl}'] = {'us': e0.elapsed_time(e1) / a.iters * 1e3, 'bit_identical_to_first': same}
         if impl == '2':
             res[f'impl{impl}']['spin_stats(total,max,waiters)'] = ns.bwd_scratch[:4 * (ns.B + 4)].view(torch.int32)[ns.B + 1:].tolist()
-    print(json.dumps({'shape': a.shape, 'batch': a.batch, 'backward': res}))
+    # plan + backward: two calls vs the one call whose gather kernel carries the plan warps
+    os.environ['FO_BWD_IMPL'] = '1'
+    combo = {}
+    for name, fn, env in (('plan_then_backward', lambda: (ns.bwd_plan_build(), ns.backward()), '1'),
+                          ('backward_with_plan_separate_launch', ns.backward_with_plan, '0'),
+                          ('backward_with_plan_riding', ns.backward_with_plan, '1')):
+        os.environ['FO_BWD_RIDE'] = env
+        ns.dg.fill_(float('nan')); ns.fg.fill_(float('nan'))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(ref[0].view(torch.int32), ns.dg.view(torch.int32)) and
+                    torch.equal(ref[1].view(torch.int32), ns.fg.view(torch.int32)))
+        combo[name] = {'us': e0.elapsed_time(e1) / a.iters * 1e3, 'grads_bit_identical': same}
+    print(json.dumps({'shape': a.shape, 'batch': a.batch, 'backward': res, 'plan_plus_backward': combo}))
 
 
 if __name__ == '__main__':
