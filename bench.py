@@ -634,7 +634,7 @@ def run_ours(args):
                 'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': e2e_ms / Ke, 'steps': Ke,
                 'chunks': e2e_chunks, 'api': 'fo_view_transform_host_calib (C ABI, pinned host buffers)',
                 'pcie_probe': pcie,
-                'wire_floor_samples_per_s': (B / max(h2d_bytes / (pcie['h2d_GBps'] * 1e9), d2h_bytes / (pcie['d2h_GBps'] * 1e9))
+                'wire_floor_samples_per_s_per_gpu': (B / max(h2d_bytes / (pcie['h2d_GBps'] * 1e9), d2h_bytes / (pcie['d2h_GBps'] * 1e9))
                                              if isinstance(pcie, dict) and 'h2d_GBps' in pcie else None),
                 'note': 'every rank moves its own bytes through the host; the box-wide host<->device throughput, not '
                         'the kernels, bounds this figure from two GPUs on'},

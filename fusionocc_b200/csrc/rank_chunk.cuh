@@ -277,6 +277,77 @@ __global__ void __launch_bounds__(kChunkThreads, 3) chunk_voxelize_kernel(ChunkA
 static_assert(kChunkVox == 1024, "the kernels shift by 10");
 
 // ------------------------------------------------------------------------------------------------
+// The same camera-major point loop feeding the global bucket sort of bucket_sort.cuh (its count pass): voxel id +
+// arrival slot.  PPT points per thread, CTAs of 256 threads = 256 * PPT consecutive frustum points of ONE camera.
+// ------------------------------------------------------------------------------------------------
+#ifndef FO_VOXCAM_PPT
+#define FO_VOXCAM_PPT 2
+#endif
+#ifndef FO_VOXCAM_MINB
+#define FO_VOXCAM_MINB 6
+#endif
+template <bool CALIB>
+__global__ void __launch_bounds__(kChunkThreads, FO_VOXCAM_MINB) voxelize_count_cam_kernel(VoxArgs v, CalibArgs g, int n_cams,
+                                                                                        int dhw) {
+    constexpr int PPT = FO_VOXCAM_PPT;
+    const int tid = threadIdx.x;
+    const int bn = blockIdx.y;
+    const int b = bn / n_cams;
+    if (blockIdx.x == 0 && bn == 0 && tid == 0) {
+        v.hdr->flags = 0;
+        v.hdr->n_subs = v.n_subs;
+        v.hdr->subs_per_sample = v.subs_per_sample;
+        v.hdr->structured = 1;
+        v.hdr->fwd_heavy[0] = v.hdr->fwd_heavy[1] = v.hdr->fwd_heavy[2] = 0;
+    }
+    CamMats cm;
+    if (CALIB) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) cm.m[i] = __ldg(g.cam + 24 * bn + i);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cm.bd[i] = __ldg(g.bda + 12 * b + i);
+    }
+    const int p_cam = bn * dhw;
+    const int c0 = blockIdx.x * (kChunkThreads * PPT);
+    const int bV = b * (v.X * v.Y * v.Z);
+    const float rx = __frcp_rn(v.ivx), ry = __frcp_rn(v.ivy), rz = __frcp_rn(v.ivz);
+    int key[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int r = c0 + tid + k * kChunkThreads;
+        key[k] = -2;
+        if (r >= dhw) continue;
+        const int p = p_cam + r;
+        float x, y, z;
+        if (CALIB) {
+            const float *f = g.frustum + 3 * r;
+            calib_point_cam(cm, g.mode, g.bda_has_t != 0, __ldg(f), __ldg(f + 1), __ldg(f + 2), x, y, z);
+            if (g.coor_out) {
+                float *o = g.coor_out + 3 * (int64_t)p;
+                o[0] = x; o[1] = y; o[2] = z;
+            }
+        } else {
+            const float *cc = v.coor + 3 * (int64_t)p;
+            x = __ldcs(cc); y = __ldcs(cc + 1); z = __ldcs(cc + 2);
+        }
+        const long long ix = axis_index(x, v.lbx, v.ivx, rx), iy = axis_index(y, v.lby, v.ivy, ry),
+                        iz = axis_index(z, v.lbz, v.ivz, rz);
+        key[k] = (ix >= 0 && ix < v.X && iy >= 0 && iy < v.Y && iz >= 0 && iz < v.Z)
+                     ? bV + ((int)iz * v.Y + (int)iy) * v.X + (int)ix : -1;
+    }
+    int slot[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) slot[k] = key[k] >= 0 ? atomicAdd(v.cnt + key[k], 1) : 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        if (key[k] == -2) continue;
+        const int p = p_cam + c0 + tid + k * kChunkThreads;
+        v.key[p] = key[k];
+        v.slot[p] = slot[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A2: multisplit of the kept points into per-chunk lists.   grid = (blocks per camera, B * N)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kChunkThreads) chunk_scatter_kernel(ChunkArgs a) {

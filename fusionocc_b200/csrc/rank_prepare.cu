@@ -530,7 +530,16 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     va.X = X; va.Y = Y; va.Z = Z;
     va.cnt = ss.cnt; va.key = key; va.slot = slot;
     va.hdr = pv.hdr; va.n_subs = (int)n_subs; va.subs_per_sample = sps;
-    if (calib) voxelize_count_kernel<true><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, *calib);
+    // FO_VOX_IMPL (A/B): 0 = round-1 point loop (per-point calibration loads, point -> camera division, IEEE divisions),
+    // 1 = one camera per CTA: calibration in registers, division only near voxel boundaries
+    const char *ve = getenv("FO_VOX_IMPL");
+    const int vox_impl = (ve && *ve) ? atoi(ve) : (calib ? 1 : 0);
+    if (vox_impl >= 1 && (int64_t)B * N <= 65535) {
+        const int dhw = D * H * W, per = kChunkThreads * FO_VOXCAM_PPT;
+        const dim3 grid_v((unsigned)((dhw + per - 1) / per), (unsigned)(B * N));
+        if (calib) voxelize_count_cam_kernel<true><<<grid_v, kChunkThreads, 0, stream>>>(va, *calib, N, dhw);
+        else voxelize_count_cam_kernel<false><<<grid_v, kChunkThreads, 0, stream>>>(va, CalibArgs{}, N, dhw);
+    } else if (calib) voxelize_count_kernel<true><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, *calib);
     else voxelize_count_kernel<false><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, CalibArgs{});
     FO_LAUNCH_CHECK("voxelize_count_kernel");
 
