@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(LIB_DIR, f'libfusionocc_b200{_SUFFIX}.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 SOURCES = ['cabi.cu', 'rank_prepare.cu', 'bev_pool_fwd.cu', 'bev_pool_bwd.cu', 'lift_prepare.cu']
-HEADERS = ['common.cuh', 'bucket_sort.cuh', 'tma.cuh', 'rank_chunk.cuh', 'bwd_plan.cuh']
+HEADERS = ['common.cuh', 'bucket_sort.cuh', 'tma.cuh', 'rank_chunk.cuh', 'bwd_plan.cuh', 'rank_fast.cuh']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -453,6 +453,8 @@ __device__ __forceinline__ void pixel_warp(const PixelArgs &a, float *wsm, const
 template <int LPR, bool FULL>
 __global__ void __launch_bounds__(kPix2Threads, FO_PIX2_MINB) bwd_pixel2_kernel(PixelArgs a) {
     extern __shared__ __align__(16) float psm[];
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PPW = 32 / LPR;
     const int n = a.n_bwd_dev ? min(max(*a.n_bwd_dev, 0), (int)a.n_bwd) : (int)a.n_bwd;
@@ -511,6 +513,8 @@ template <int NACC, bool EXACT>
 __global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const __grid_constant__ CUtensorMap tm) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ __align__(8) unsigned long long s_bar[8];
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (__ldg(&a.hdr->flags) & kFlagUnsorted) return;            // the per-interval gather runs instead
     const int C = EXACT ? 32 * NACC : a.C;
@@ -548,6 +552,8 @@ __global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, P
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ __align__(8) unsigned long long s_bar[8];
     __shared__ int s_cmp[8][32 * R];
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long T = (long long)p.n_plan_ctas + p.n_gather_ctas;
     const int bid = blockIdx.x;
@@ -750,7 +756,7 @@ int launch_pixel2(const PixelArgs &pa, cudaStream_t stream) {
     do {                                                                                                          \
         if (smem > 48 * 1024)                                                                                     \
             FO_CUDA(cudaFuncSetAttribute(bwd_pixel2_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        bwd_pixel2_kernel<L, F><<<(unsigned)blocks, kPix2Threads, smem, stream>>>(pa);                            \
+        FO_CUDA(launch_pdl(kPdlPixel, bwd_pixel2_kernel<L, F>, dim3((unsigned)blocks), dim3(kPix2Threads), smem, stream, pa)); \
     } while (0)
     const bool full = C == 4 * lpr;
     if (lpr == 8) { if (full) FO_PIX2(8, true); else FO_PIX2(8, false); }
@@ -779,8 +785,14 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
     FO_CHECK_ARG(depth_grad && feat_grad, "NULL gradient output");
     FO_CHECK_ARG(n_depth >= 0 && n_feat_rows >= 1 && n_points >= 0 && n_intervals >= 0, "negative size");
     FO_CHECK_ARG(n_points < INT_MAX && (int64_t)B * n_vox < INT_MAX && n_depth < INT_MAX, "sizes exceed int32 ranks");
-    FO_CUDA(cudaMemsetAsync(depth_grad, 0, (size_t)n_depth * 4, stream));
-    FO_CUDA(cudaMemsetAsync(feat_grad, 0, (size_t)n_feat_rows * c * 4, stream));
+    // zero-fill of both gradients (points outside the grid / pixels without points are never written below)
+    if ((((uintptr_t)depth_grad | (uintptr_t)feat_grad) & 15) == 0 && n_depth % 4 == 0 && (n_feat_rows * c) % 4 == 0) {
+        FO_CUDA(launch_pdl(kPdlZero, zero2_kernel, dim3(grid_for(n_depth / 4 + n_feat_rows * c / 4, 256, 8)), dim3(256), 0, stream,
+                           (uint4 *)depth_grad, n_depth / 4, (uint4 *)feat_grad, n_feat_rows * c / 4));
+    } else {
+        FO_CUDA(cudaMemsetAsync(depth_grad, 0, (size_t)n_depth * 4, stream));
+        FO_CUDA(cudaMemsetAsync(feat_grad, 0, (size_t)n_feat_rows * c * 4, stream));
+    }
     // a requested plan rides along the gather when it can (below); otherwise it is built first, as a separate launch
     bool plan_pending = req != nullptr;
     auto build_plan_now = [&]() -> int {
@@ -859,7 +871,8 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         if (g_smem > 48 * 1024)                                                                                       \
             FO_CUDA(cudaFuncSetAttribute(bwd_gather_plan_kernel<NA, EX, RR>,                                          \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));                  \
-        bwd_gather_plan_kernel<NA, EX, RR><<<(unsigned)(pr.n_gather_ctas + pr.n_plan_ctas), 256, g_smem, stream>>>(ga, pr, tm); \
+        FO_CUDA(launch_pdl(kPdlGather, bwd_gather_plan_kernel<NA, EX, RR>, dim3((unsigned)(pr.n_gather_ctas + pr.n_plan_ctas)),   \
+                           dim3(256), g_smem, stream, ga, pr, tm));                                                   \
     } while (0)
 #define FO_GRIDE_R(NA, EX)                                                                                            \
     do {                                                                                                              \
@@ -882,7 +895,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         if (g_smem > 48 * 1024)                                                                                    \
             FO_CUDA(cudaFuncSetAttribute(bwd_gather_tma_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)g_smem));                                                            \
-        bwd_gather_tma_kernel<NA, EX><<<dim3(gu, B), 256, g_smem, stream>>>(ga, tm);                               \
+        FO_CUDA(launch_pdl(kPdlGather, bwd_gather_tma_kernel<NA, EX>, dim3(gu, B), dim3(256), g_smem, stream, ga, tm));        \
     } while (0)
                 if (nacc == 1) { if (exact) FO_GTMA(1, true); else FO_GTMA(1, false); }
                 else if (nacc == 2) { if (exact) FO_GTMA(2, true); else FO_GTMA(2, false); }

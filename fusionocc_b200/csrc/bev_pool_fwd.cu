@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
     float *smem = TMAST ? reinterpret_cast<float *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023) : smem_raw;
     __shared__ __align__(16) int s_rx[32 + 8];           // (feature row << 5 | voxel slot) per point
     __shared__ __align__(16) float s_rd[32 + 8];         // depth value per point
+    pdl_wait();
+    pdl_launch();
 
     const int lane = threadIdx.x;
     const int C = EXACT ? 32 * NACC : a.C;
@@ -422,15 +424,13 @@ int launch_dense(const FwdArgs &a, int n_ctas, size_t smem, cudaStream_t stream,
         auto kern = fwd_dense_kernel<NACC, EXACT, FO_LAYOUT_BCZYX, true>;
         const size_t sm2 = smem + 1024;
         if (sm2 > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        kern<<<dim3(a.B, n_ctas + a.front_y), 32, sm2, stream>>>(a, *tm);
-        FO_LAUNCH_CHECK("fwd_dense_kernel<tma>");
+        FO_CUDA(launch_pdl(kPdlFwd, kern, dim3(a.B, n_ctas + a.front_y), dim3(32), sm2, stream, a, *tm));
         return FO_OK;
     }
     auto kern = fwd_dense_kernel<NACC, EXACT, LAYOUT, false>;
     if (smem > 48 * 1024) FO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap dummy{};
-    kern<<<dim3(a.B, n_ctas + a.front_y), 32, smem, stream>>>(a, dummy);
-    FO_LAUNCH_CHECK("fwd_dense_kernel");
+    FO_CUDA(launch_pdl(kPdlFwd, kern, dim3(a.B, n_ctas + a.front_y), dim3(32), smem, stream, a, dummy));
     return FO_OK;
 }
 template <int LAYOUT>

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kScanThreads) tile_reduce_kernel(const int32_t
                                                                    unsigned long long *__restrict__ agg,
                                                                    unsigned long long *__restrict__ agg_group) {
     __shared__ unsigned long long s_red[kScanThreads / 32];
+    pdl_wait();
+    pdl_launch();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * kScanTile;
     unsigned long long mine = 0;
@@ -94,6 +96,8 @@ struct ScanArgs {
 __global__ void __launch_bounds__(kScanThreads) scan_buckets_kernel(ScanArgs a) {
     __shared__ unsigned long long s_warp[kScanThreads / 32];
     __shared__ unsigned long long s_red[kScanThreads / 32];
+    pdl_wait();
+    pdl_launch();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int64_t base = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
@@ -320,6 +324,8 @@ constexpr int kWarpSortMax = 128; // ... up to this length by one warp in regist
 
 template <bool kForward>
 __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
+    pdl_wait();
+    pdl_launch();
     const int n = *a.n_intervals;
     const int stride = gridDim.x * blockDim.x;
     if (kForward && a.heavy_list != nullptr)
@@ -375,6 +381,8 @@ __device__ inline void cta_sort_segment(int32_t *seg, int len, int *smem) {
 template <bool kForward>
 __global__ void __launch_bounds__(kSortThreads) order_long_kernel(OrderArgs a) {
     __shared__ int s_sort[kSortSmemCta];
+    pdl_wait();
+    pdl_launch();
     const int n = a.long_count[0], n_big = a.long_count[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = gridDim.x * (kSortThreads / 32);

@@ -5,6 +5,7 @@
 #include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/fusionocc_b200.h"
 
@@ -226,6 +227,58 @@ inline int grid_for(int64_t work_items, int per_block, int ctas_per_sm = FO_GRID
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  One step is ~14 short kernels on one stream; launched back to back each pays its
+// launch latency and its fill / drain ramp (~3 us per boundary, a third of the rank precompute at batch 1).  Every
+// hot-path kernel therefore starts with  pdl_wait(); pdl_launch();  and is launched with the programmatic-stream-
+// serialization attribute: the NEXT kernel's CTAs become resident while this one drains and block in pdl_wait() until
+// this grid has completed and its memory is visible — same ordering as a plain stream, without the bubble.
+// FO_PDL=0 turns the attribute off (A/B runs); the device instructions are no-ops in a plain launch.
+// ----------------------------------------------------------------------------------------------
+// FO_PDL is a bit mask over kernel groups (A/B runs): 1 rank pipeline, 2 forward, 4 backward gather (+ plan),
+// 8 backward pixel kernel, 16 zero-fill kernels; default: all.
+enum { kPdlRank = 1, kPdlFwd = 2, kPdlGather = 4, kPdlPixel = 8, kPdlZero = 16 };
+inline bool pdl_enabled(int group) {
+    const char *e = getenv("FO_PDL");
+    const int mask = (e && *e) ? atoi(e) : 31;
+    return (mask & group) != 0;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef FO_PDL_EARLY
+#define FO_PDL_EARLY 0      // 1: every CTA releases the dependent grid at its start; 0: only at its exit (implicit)
+#endif
+__device__ __forceinline__ void pdl_launch() {
+#if FO_PDL_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int group, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled(group) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Args &&>(args)...);
+}
+
+// zero-fills up to two 16-byte aligned regions (counters / gradient outputs) as a kernel of the same stream, so that
+// it takes part in the programmatic launch chain (a memset node would serialise it)
+static __global__ void __launch_bounds__(256) zero2_kernel(uint4 *a, int64_t na16, uint4 *b, int64_t nb16) {
+    pdl_wait();
+    pdl_launch();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = gtid; i < na16; i += stride) a[i] = z;
+    for (int64_t i = gtid; i < nb16; i += stride) b[i] = z;
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Division of a 32-bit unsigned by a run-time invariant divisor (Granlund & Montgomery, "Division by invariant

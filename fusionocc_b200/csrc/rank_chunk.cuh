@@ -290,6 +290,8 @@ template <bool CALIB>
 __global__ void __launch_bounds__(kChunkThreads, FO_VOXCAM_MINB) voxelize_count_cam_kernel(VoxArgs v, CalibArgs g, int n_cams,
                                                                                         int dhw) {
     constexpr int PPT = FO_VOXCAM_PPT;
+    pdl_wait();
+    pdl_launch();
     const int tid = threadIdx.x;
     const int bn = blockIdx.y;
     const int b = bn / n_cams;

@@ -1,0 +1,243 @@
+// fusionocc_b200 — forward-flavour rank pipeline, second cut of the scan and order passes (sm_100a).
+//
+// Same one-digit bucket sort as bucket_sort.cuh (count -> scan -> place -> order within bucket) and the same
+// bits out (profiles/r02_summary.md §7):
+//
+//   * the scan's per-interval outputs (interval_starts / interval_lengths / iv_vox) used to be written from the
+//     sequential per-thread walk, one predicated 4-byte store per bucket and array; they are now staged in shared
+//     memory in interval order and leave as full lines (33 -> 26 us at batch 8);
+//   * the scan classifies the intervals while it has their lengths in registers and queues those of more than
+//     kLaneSortMax points (9..128: one warp each; longer: one CTA each), so that ONE order launch does everything:
+//     the queued intervals first, then one lane per short interval (the former order_short + order_long pair).
+//
+// Measured and NOT kept: a placement that writes all three rank arrays at the point's final position, with an
+// order pass over only the >= 2-point intervals (82 % of the occupied voxels hold ONE point).  Every scattered
+// 4-byte store per point costs a 32-byte sector write: place 16.5 -> 34.4 us, order 29.7 -> 19.5 us — a net loss
+// (and 291 -> 352 us at 512x1408, where there are 2.5 points per voxel).
+#pragma once
+
+#include "bucket_sort.cuh"
+
+namespace fo {
+
+constexpr int kScan2Threads = 256;
+constexpr int kScan2Items   = kScanTile / kScan2Threads;      // 8 buckets per thread
+static_assert(kScan2Items == 8 && kScanTile == 2048, "scan2 is written for 2048-bucket tiles, 256 threads x 8");
+
+struct ListArgs {
+    int32_t *long_list;      // intervals of kLaneSortMax+1 .. kWarpSortMax points from the front, longer ones from the END
+    int32_t *counts;         // zero-initialised: [1] long (front), [2] long (end)
+    int32_t long_cap;
+};
+
+__global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a, ListArgs l) {
+    __shared__ unsigned long long s_warp[kScan2Threads / 32];
+    __shared__ unsigned long long s_red[kScan2Threads / 32];
+    __shared__ int s_st[kScanTile], s_ln[kScanTile], s_vx[kScanTile];
+    __shared__ int s_q[kScanTile / 8];       // tile-local queue of long intervals (> 8 points each, 2048 buckets)
+    __shared__ int s_qn, s_qbase;
+    pdl_wait();
+    pdl_launch();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int64_t base = (int64_t)tile * kScanTile + (int64_t)tid * kScan2Items;
+    if (tid == 0) s_qn = 0;
+
+    unsigned long long pre = 0;
+    const int g0 = tile / kScanGroup;
+    for (int g = tid; g < g0; g += kScan2Threads) pre += a.agg_group[g];
+    if (tid < tile - g0 * kScanGroup) pre += a.agg[g0 * kScanGroup + tid];
+
+    int c[kScan2Items];
+    if (base + kScan2Items <= a.n_buckets) {
+        const int4 *src = reinterpret_cast<const int4 *>(a.cnt + base);
+        const int4 v0 = src[0], v1 = src[1];
+        c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y; c[6] = v1.z; c[7] = v1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScan2Items; ++j) c[j] = (base + j < a.n_buckets) ? a.cnt[base + j] : 0;
+    }
+    unsigned long long mine = 0;                // (pts << 32) | ne
+#pragma unroll
+    for (int j = 0; j < kScan2Items; ++j)
+        mine += ((unsigned long long)(unsigned)c[j] << 32) | (c[j] > 0 ? 1ull : 0ull);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_red[warp] = pre;
+    __syncthreads();
+    unsigned long long warp_off = 0, tile_prefix = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScan2Threads / 32; ++w) {
+        if (w < warp) warp_off += s_warp[w];
+        tile_prefix += s_red[w];
+        tile_total += s_warp[w];
+    }
+    const unsigned long long run = tile_prefix + warp_off + (incl - mine);
+    unsigned pts = (unsigned)(run >> 32), ne = (unsigned)(run & 0xffffffffu);
+    const int ne0 = (int)(tile_prefix & 0xffffffffu);          // first interval of this tile
+    const int n_tile = (int)(tile_total & 0xffffffffu);        // intervals of this tile
+
+    int64_t vin = 0, sample = 0;
+    const bool want_tiles = a.sub_iv != nullptr;
+    if (want_tiles) { sample = base / a.vox_per_sample; vin = base - sample * a.vox_per_sample; }
+
+    int o[kScan2Items], iv[kScan2Items];
+#pragma unroll
+    for (int j = 0; j < kScan2Items; ++j) {
+        const int64_t v = base + j;
+        o[j] = (int)pts;
+        iv[j] = (int)ne;
+        if (v < a.n_buckets) {
+            if (want_tiles) {
+                if ((vin & (kSub - 1)) == 0) {
+                    const int64_t u = sample * a.subs_per_sample + (vin >> kSubShift);
+                    a.sub_iv[u] = (int)ne;
+                    a.sub_pt[u] = (int)pts;
+                }
+                if (++vin == a.vox_per_sample) { vin = 0; ++sample; }
+            }
+            if (c[j] > 0) {
+                const int li = (int)ne - ne0;
+                s_st[li] = (int)pts;
+                s_ln[li] = c[j];
+                s_vx[li] = (int)v;
+                pts += (unsigned)c[j];
+                ++ne;
+            }
+        }
+    }
+    if (base + kScan2Items <= a.n_buckets) {
+        int4 *dst = reinterpret_cast<int4 *>(a.cnt + base);
+        dst[0] = make_int4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_int4(o[4], o[5], o[6], o[7]);
+        if (a.bucket2iv) {
+            int4 *d2 = reinterpret_cast<int4 *>(a.bucket2iv + base);
+            d2[0] = make_int4(iv[0], iv[1], iv[2], iv[3]);
+            d2[1] = make_int4(iv[4], iv[5], iv[6], iv[7]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScan2Items; ++j)
+            if (base + j < a.n_buckets) {
+                a.cnt[base + j] = o[j];
+                if (a.bucket2iv) a.bucket2iv[base + j] = iv[j];
+            }
+    }
+    if (base <= a.n_buckets - 1 && a.n_buckets - 1 < base + kScan2Items) {
+        a.totals[0] = (int)pts;
+        a.totals[1] = (int)ne;
+        if (want_tiles) { a.sub_iv[a.n_subs] = (int)ne; a.sub_pt[a.n_subs] = (int)pts; }
+        if (a.fwd_hdr) a.fwd_hdr->n_intervals = (int)ne;
+        if (a.bwd_hdr) { a.bwd_hdr->n_bwd_intervals = (int)ne; a.bwd_hdr->n_points = (int)pts; }
+    }
+    __syncthreads();
+    // compact per-interval outputs: full lines; classification of the intervals that need ordering
+    for (int i = tid; i < n_tile; i += kScan2Threads) {
+        const int len = s_ln[i];
+        a.iv_starts[ne0 + i] = s_st[i];
+        a.iv_lengths[ne0 + i] = len;
+        if (a.iv_bucket) a.iv_bucket[ne0 + i] = s_vx[i];
+        if (len > kLaneSortMax) {
+            if (len <= kWarpSortMax) {
+                const int at = atomicAdd(&s_qn, 1);
+                if (at < kScanTile / 8) s_q[at] = ne0 + i;
+                else {                                   // a tile with more than 256 long intervals: straight to the global queue
+                    const int g = atomicAdd(l.counts + 1, 1);
+                    if (g < l.long_cap) l.long_list[g] = ne0 + i;
+                }
+            } else {
+                const int at = atomicAdd(l.counts + 2, 1);
+                if (at < l.long_cap) l.long_list[l.long_cap - 1 - at] = ne0 + i;
+            }
+        }
+    }
+    __syncthreads();
+    const int nl = min(s_qn, kScanTile / 8);
+    if (tid == 0 && nl > 0) s_qbase = atomicAdd(l.counts + 1, nl);
+    __syncthreads();
+    for (int i = tid; i < nl; i += kScan2Threads)
+        if (s_qbase + i < l.long_cap) l.long_list[s_qbase + i] = s_q[i];
+}
+
+struct Order2Args {
+    int32_t *sorted;            // ranks_depth (in/out)
+    int32_t *ranks_feat, *ranks_bev;
+    const int32_t *iv_starts, *iv_lengths, *iv_bucket;
+    const int32_t *n_intervals; // device count
+    ListArgs l;
+    FastDiv dhw, hw;
+    const int32_t *sub_pt;      // dense sub-tile list of the forward plan
+    int32_t n_subs;
+    int32_t *heavy_list, *heavy_n;
+};
+
+// One launch for the whole order pass: (1) queued long intervals, one warp each; (2) the forward plan's list of dense
+// sub-tiles; (3) every interval of up to kLaneSortMax points, one lane each; (4) very long intervals, one CTA each.
+__global__ void __launch_bounds__(kSortThreads) order2_kernel(Order2Args a) {
+    __shared__ int s_sort[kSortSmemCta];
+    pdl_wait();
+    pdl_launch();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gtid = blockIdx.x * kSortThreads + threadIdx.x, stride = gridDim.x * kSortThreads;
+    const int n_big = min(a.l.counts[2], a.l.long_cap);
+    const int n_long = min(a.l.counts[1], a.l.long_cap - n_big);
+    const int nwarps = gridDim.x * (kSortThreads / 32);
+    for (int w = blockIdx.x * (kSortThreads / 32) + warp; w < n_long; w += nwarps) {
+        const int k = a.l.long_list[w];
+        const int ls = a.iv_starts[k], ll = a.iv_lengths[k], lb = a.iv_bucket[k];
+        warp_sort_segment(a.sorted + ls, ll, nullptr, lane);
+        __syncwarp();
+        for (int j = lane; j < ll; j += 32) {
+            a.ranks_feat[ls + j] = feat_row_of(a.sorted[ls + j], a.dhw, a.hw);
+            a.ranks_bev[ls + j] = lb;
+        }
+        __syncwarp();
+    }
+    if (a.heavy_list != nullptr)
+        for (int u = gtid; u < a.n_subs; u += stride)
+            if (a.sub_pt[u + 1] - a.sub_pt[u] > kHeavyPts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
+    const int n = *a.n_intervals;
+    for (int k = gtid; k < n; k += stride) {
+        const int s = a.iv_starts[k], len = a.iv_lengths[k];
+        if (len > kLaneSortMax) continue;
+        const int bucket = a.iv_bucket[k];
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
+        if (len > 1) sort8(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < len) {
+                if (len > 1) a.sorted[s + j] = v[j];
+                a.ranks_feat[s + j] = feat_row_of(v[j], a.dhw, a.hw);
+                a.ranks_bev[s + j] = bucket;
+            }
+    }
+    if (n_big == 0) return;
+    __syncthreads();
+    for (int w = blockIdx.x; w < n_big; w += gridDim.x) {
+        const int k = a.l.long_list[a.l.long_cap - 1 - w];
+        const int ls = a.iv_starts[k], ll = a.iv_lengths[k], lb = a.iv_bucket[k];
+        if (ll <= kSortSmemCta) {
+            cta_sort_segment(a.sorted + ls, ll, s_sort);
+        } else {
+            if (warp == 0) warp_sort_segment(a.sorted + ls, ll, nullptr, lane);
+            __threadfence_block();
+            __syncthreads();
+        }
+        for (int j = threadIdx.x; j < ll; j += kSortThreads) {
+            a.ranks_feat[ls + j] = feat_row_of(a.sorted[ls + j], a.dhw, a.hw);
+            a.ranks_bev[ls + j] = lb;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace fo

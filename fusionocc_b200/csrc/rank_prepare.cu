@@ -7,6 +7,7 @@
 
 #include "bucket_sort.cuh"
 #include "bwd_plan.cuh"
+#include "rank_fast.cuh"
 
 namespace fo {
 
@@ -88,6 +89,8 @@ __device__ __forceinline__ void calib_point(const CalibArgs &g, int p, float &ox
 
 template <bool CALIB>
 __global__ void __launch_bounds__(256) voxelize_count_kernel(VoxArgs a, CalibArgs g) {
+    pdl_wait();
+    pdl_launch();
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid == 0) {
         a.hdr->flags = 0;
@@ -165,6 +168,8 @@ __global__ void __launch_bounds__(256) place_kernel(const int32_t *__restrict__ 
                                                     const int32_t *__restrict__ offs, int64_t n_cap,
                                                     const int32_t *__restrict__ n_dev, int64_t n_buckets,
                                                     int32_t *__restrict__ sorted) {
+    pdl_wait();
+    pdl_launch();
     const int64_t n = n_dev ? min((int64_t)max(*n_dev, 0), n_cap) : n_cap;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -430,7 +435,9 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
 
 extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total) {
     if (n_points_total < 0 || n_voxels_total < 0) return 0;
-    const size_t legacy = bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256);
+    // counters + aggregates | slot[P] | long-interval queue of the order pass [P/8 + 1]
+    const size_t legacy = bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256) +
+                          (size_t)align_up((n_points_total / 8 + 1) * 4, 256);
     const size_t chunked = chunk_scratch_view(nullptr, chunk_bound(n_voxels_total), n_points_total).total_bytes;
     return legacy > chunked ? legacy : chunked;
 }
@@ -520,8 +527,14 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     int32_t *slot = (int32_t *)((char *)scratch + ss.zero_bytes);
     int32_t *key = pv.pt2vox;                    // voxel id of every frustum point, -1 if outside the grid
 
-    FO_CUDA(cudaMemsetAsync(scratch, 0, ss.zero_bytes, stream));
-    FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
+    // zero the counters / aggregates and the four count words (counts_dev: 16-byte aligned like every tensor base)
+    if (((uintptr_t)counts_dev & 15) == 0) {
+        FO_CUDA(launch_pdl(kPdlZero, zero2_kernel, dim3(grid_for((int64_t)(ss.zero_bytes / 16), 256, 8)), dim3(256), 0, stream,
+                           (uint4 *)scratch, (int64_t)(ss.zero_bytes / 16), (uint4 *)counts_dev, (int64_t)1));
+    } else {
+        FO_CUDA(cudaMemsetAsync(scratch, 0, ss.zero_bytes, stream));
+        FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
+    }
 
     VoxArgs va;
     va.coor = coor; va.n_points = P; va.points_per_sample = pps;
@@ -537,10 +550,10 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     if (vox_impl >= 1 && (int64_t)B * N <= 65535) {
         const int dhw = D * H * W, per = kChunkThreads * FO_VOXCAM_PPT;
         const dim3 grid_v((unsigned)((dhw + per - 1) / per), (unsigned)(B * N));
-        if (calib) voxelize_count_cam_kernel<true><<<grid_v, kChunkThreads, 0, stream>>>(va, *calib, N, dhw);
-        else voxelize_count_cam_kernel<false><<<grid_v, kChunkThreads, 0, stream>>>(va, CalibArgs{}, N, dhw);
-    } else if (calib) voxelize_count_kernel<true><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, *calib);
-    else voxelize_count_kernel<false><<<grid_for((P + 3) / 4, 256), 256, 0, stream>>>(va, CalibArgs{});
+        if (calib) FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw));
+        else FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<false>, grid_v, dim3(kChunkThreads), 0, stream, va, CalibArgs{}, N, dhw));
+    } else if (calib) FO_CUDA(launch_pdl(kPdlRank, voxelize_count_kernel<true>, dim3(grid_for((P + 3) / 4, 256)), dim3(256), 0, stream, va, *calib));
+    else FO_CUDA(launch_pdl(kPdlRank, voxelize_count_kernel<false>, dim3(grid_for((P + 3) / 4, 256)), dim3(256), 0, stream, va, CalibArgs{}));
     FO_LAUNCH_CHECK("voxelize_count_kernel");
 
     ScanArgs sa;
@@ -553,27 +566,45 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     sa.fwd_hdr = pv.hdr; sa.bwd_hdr = nullptr;
     sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((NV + kScanTile - 1) / kScanTile);
-    tile_reduce_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(ss.cnt, NV, ss.agg, ss.agg_group);
-    FO_LAUNCH_CHECK("tile_reduce_kernel");
-    scan_buckets_kernel<<<scan_blocks, kScanThreads, 0, stream>>>(sa);
-    FO_LAUNCH_CHECK("scan_buckets_kernel");
+    FO_CUDA(launch_pdl(kPdlRank, tile_reduce_kernel, dim3(scan_blocks), dim3(kScanThreads), 0, stream, (const int32_t *)ss.cnt, NV,
+                       ss.agg, ss.agg_group));
 
-    place_kernel<<<grid_for(P, 256), 256, 0, stream>>>(key, slot, ss.cnt, P, nullptr, NV, ranks_depth);
-    FO_LAUNCH_CHECK("place_kernel");
+    // FO_RANK_FAST (A/B): 1 (default) = scan with staged outputs and a queue of the long intervals + ONE order launch;
+    // 0 = the round-1 passes (scan, order_short queueing the long intervals, order_long)
+    const char *fe = getenv("FO_RANK_FAST");
+    const int fast = (fe && *fe) ? atoi(fe) : 1;
+    const FastDiv fd_dhw = make_fastdiv((uint32_t)(D * H * W)), fd_hw = make_fastdiv((uint32_t)(H * W));
+    if (fast >= 1) {
+        // long-interval queue: lives behind the slot array (both are live until the placement has run)
+        ListArgs la;
+        la.long_list = (int32_t *)((char *)slot + align_up(P * 4, 256)); la.long_cap = (int32_t)(P / 8 + 1);
+        la.counts = ss.counter;
+        FO_CUDA(launch_pdl(kPdlRank, scan_buckets2_kernel, dim3(scan_blocks), dim3(kScan2Threads), 0, stream, sa, la));
+        FO_CUDA(launch_pdl(kPdlRank, place_kernel, dim3(grid_for(P, 256)), dim3(256), 0, stream, (const int32_t *)key,
+                           (const int32_t *)slot, (const int32_t *)ss.cnt, P, (const int32_t *)nullptr, NV, ranks_depth));
+        Order2Args o2;
+        o2.sorted = ranks_depth; o2.ranks_feat = ranks_feat; o2.ranks_bev = ranks_bev; o2.iv_starts = interval_starts;
+        o2.iv_lengths = interval_lengths; o2.iv_bucket = pv.iv_vox; o2.n_intervals = counts_dev + 1;
+        o2.l = la; o2.dhw = fd_dhw; o2.hw = fd_hw;
+        o2.sub_pt = pv.sub_pt; o2.n_subs = (int32_t)n_subs; o2.heavy_list = pv.heavy_list; o2.heavy_n = pv.hdr->fwd_heavy;
+        FO_CUDA(launch_pdl(kPdlRank, order2_kernel, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
+        return FO_OK;
+    }
+    FO_CUDA(launch_pdl(kPdlRank, scan_buckets_kernel, dim3(scan_blocks), dim3(kScanThreads), 0, stream, sa));
+    FO_CUDA(launch_pdl(kPdlRank, place_kernel, dim3(grid_for(P, 256)), dim3(256), 0, stream, (const int32_t *)key,
+                       (const int32_t *)slot, (const int32_t *)ss.cnt, P, (const int32_t *)nullptr, NV, ranks_depth));
 
     OrderArgs oa;
     oa.sorted = ranks_depth; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev;
     oa.sub_pt = pv.sub_pt; oa.n_subs = (int32_t)n_subs; oa.heavy_list = pv.heavy_list; oa.heavy_n = pv.hdr->fwd_heavy;
-    oa.dhw = make_fastdiv((uint32_t)(D * H * W)); oa.hw = make_fastdiv((uint32_t)(H * W));
+    oa.dhw = fd_dhw; oa.hw = fd_hw;
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     oa.long_cap = (int32_t)P;
     const int64_t cap_iv = P < NV ? P : NV;
-    order_short_kernel<true><<<grid_for(cap_iv, 256), 256, 0, stream>>>(oa);
-    FO_LAUNCH_CHECK("order_short_kernel<fwd>");
-    order_long_kernel<true><<<sm_count() * 16, kSortThreads, 0, stream>>>(oa);
-    FO_LAUNCH_CHECK("order_long_kernel<fwd>");
+    FO_CUDA(launch_pdl(kPdlRank, order_short_kernel<true>, dim3(grid_for(cap_iv, 256)), dim3(256), 0, stream, oa));
+    FO_CUDA(launch_pdl(kPdlRank, order_long_kernel<true>, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, oa));
     return FO_OK;
 }
 }  // namespace

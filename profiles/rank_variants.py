@@ -23,14 +23,17 @@ def main():
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--iters', type=int, default=50)
     ap.add_argument('--impls', default='0,1')
+    ap.add_argument('--fast', default='0,1', help='FO_RANK_FAST values to compare (with FO_RANK_IMPL=0)')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     vt, coor, depth, feat, og = make_inputs(SHAPES[a.shape], a.batch, 0, dev)
     ns = NativeStep(vt, coor, depth, feat, og)
     ns.setup_calib(vt, vt._bench_cal)
     res, ref = {}, None
-    for impl in a.impls.split(','):
+    variants = [(impl, '0') for impl in a.impls.split(',') if impl != '0'] + [('0', f) for f in a.fast.split(',')]
+    for impl, fast in sorted(variants, key=lambda t: (t[0] != '0', t[1])):
         os.environ['FO_RANK_IMPL'] = impl
+        os.environ['FO_RANK_FAST'] = fast
         for mode, fn in (('coor', ns.rank_prepare), ('calib', ns.rank_prepare_calib)):
             for t in (ns.rb, ns.rd, ns.rf, ns.st, ns.ln):
                 t.fill_(-7)
@@ -45,8 +48,9 @@ def main():
             torch.cuda.synchronize()
             nk, ni = (int(v) for v in ns.counts[:2].tolist())
             ns.forward()
+            ns.backward_with_plan()
             got = [ns.rb[:nk].clone(), ns.rd[:nk].clone(), ns.rf[:nk].clone(), ns.st[:ni].clone(), ns.ln[:ni].clone(),
-                   ns.out.clone()]
+                   ns.out.clone(), ns.dg.clone(), ns.fg.clone()]
             same = None
             if ref is None:
                 ref = (nk, ni, got)
@@ -55,7 +59,7 @@ def main():
             if os.environ.get('FO_SLAB_PROF_READ'):
                 prof = ns.rank_scratch[64:64 + 96].view(torch.int64).tolist()
                 print('slab_sort phases (sum cycles over CTAs, max cycles):', prof)
-            res[f'impl{impl}_{mode}'] = {'us': e0.elapsed_time(e1) / a.iters * 1e3, 'n_kept': nk, 'n_intervals': ni,
+            res[f'impl{impl}_fast{fast}_{mode}'] = {'us': e0.elapsed_time(e1) / a.iters * 1e3, 'n_kept': nk, 'n_intervals': ni,
                                          'identical_to_first': same}
     print(json.dumps({'shape': a.shape, 'batch': a.batch, 'rank_prepare': res}))
 
