@@ -283,7 +283,14 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
 // (2) GATHER ROLE with TMA.  The C x 32 block of out_grad of a sub-tile is a regular 2-D tile: one
 //     cp.async.bulk.tensor (3-D map (V, C, B), box 32 x C x 1, 128-byte swizzle) per warp replaces 8 LDG.128 +
 //     8 STS.128 per lane and their address arithmetic, and is in flight while the warp fetches its interval list.
-// (3) NOT KEPT: one fused launch (gather units of sample b+1 interleaved with pixel units of sample b, device-side
+// (3) NOT KEPT (second session, profiles/r02_summary.md §8): the rows through cp.async (LDGSTS) into a ring of three
+//     tiles per warp, two tiles ahead of the consumer, no row registers: backward 192 -> 278 us with .cg copies
+//     (every repeated row of a pixel — 1.5 points per voxel — goes back to L2), 211 us with .ca; ncu: 12 warps per SM,
+//     73 % of the stall cycles on the copies' scoreboard, 1.3 TB/s.  And an upper bound for moving depth_grad out of
+//     this kernel: with the tile stores and the depth-grad chains compiled OUT the kernel is no
+//     faster (backward 197.7 vs 192.3 us, 72 registers, 4 or 6 CTAs per SM) — its time is the two dependent index
+//     round trips and the scattered 128-byte row reads, not the chains.
+// (4) NOT KEPT: one fused launch (gather units of sample b+1 interleaved with pixel units of sample b, device-side
 //     completion counters, G consumed while L2-resident).  Measured on a B200 at the headline shape, batch 8
 //     (profiles/r02_summary.md): two launches 163 us; fused and interleaved 225 us, with a two-stage box ring per
 //     gather warp 195 us, same kernel with all gather units first 184 us; spin waits were negligible (max 42 polls).
@@ -537,6 +544,7 @@ __global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const
 // scheduler ran them back to back; as a ninth warp inside every gather CTA the plan warp outlived its CTA's gather
 // warps several times over and held their slots — profiles/r02_summary.md.)
 struct PlanRideArgs {
+    const FwdPlanHeader *fhdr;
     const int32_t *pt2vox, *vox2iv;
     int32_t D, HW, n_rows;
     int32_t n_plan_ctas, n_gather_ctas, gu;   // gu = gather CTAs per sample
@@ -566,9 +574,10 @@ __global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, P
             p.hdr->structured = 1;
         }
         const int q0 = (plans_before * 8 + warp) * kPlanPixPerWarp;
+        const int32_t *v2i = plan_vox2iv(p.fhdr, p.vox2iv);
 #pragma unroll 1
         for (int q = q0; q < min(p.n_rows, q0 + kPlanPixPerWarp); ++q)
-            plan_pixel_bitonic<R>(p.pt2vox, p.vox2iv, p.D, p.HW, q, s_cmp[warp], lane, p.ent_p, p.ent_iv, p.starts,
+            plan_pixel_bitonic<R>(p.pt2vox, v2i, p.D, p.HW, q, s_cmp[warp], lane, p.ent_p, p.ent_iv, p.starts,
                                   p.lengths, p.ids);
         return;
     }
@@ -860,7 +869,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
                                   bwd_ride_choice();
                 if (ride) {
                     PlanRideArgs pr;
-                    pr.pt2vox = pv.pt2vox; pr.vox2iv = pv.vox2iv; pr.D = D; pr.HW = req->hw; pr.n_rows = (int)n_feat_rows;
+                    pr.fhdr = pv.hdr; pr.pt2vox = pv.pt2vox; pr.vox2iv = pv.vox2iv; pr.D = D; pr.HW = req->hw; pr.n_rows = (int)n_feat_rows;
                     pr.gu = gu; pr.n_gather_ctas = gu * B;
                     pr.n_plan_ctas = (int)((n_feat_rows + 8 * kPlanPixPerWarp - 1) / (8 * kPlanPixPerWarp));
                     pr.hdr = bv.hdr; pr.ent_p = bv.ent_p; pr.ent_iv = bv.ent_iv; pr.starts = bv.starts;

@@ -6,6 +6,12 @@
 
 namespace fo {
 
+// Plans produced by the rank precompute carry either pt2vox + vox2iv (structured == 1) or, when the placement already
+// resolved the interval of every point, interval ids in the pt2vox table (structured == 2): no vox2iv gather then.
+__device__ __forceinline__ const int32_t *plan_vox2iv(const FwdPlanHeader *fhdr, const int32_t *vox2iv) {
+    return (__ldg(&fhdr->structured) == 2) ? nullptr : vox2iv;
+}
+
 // Bitonic network over packed 32-bit keys (voxel id << 7 | depth bin).  Needs B*Z*Y*X < 2^24 and D <= 128.
 // Only ~57 % of a pixel's depth bins land inside the grid, so the valid keys are first COMPACTED (ballot + popc
 // through a per-warp shared-memory row) and the network is sized to the live count: 32 / 64 / 128 elements =
@@ -23,7 +29,7 @@ __device__ __forceinline__ void plan_sort_emit(const int *cmp, const int n, cons
         const int e = 32 * r + lane;
         if (e < n) {
             ent_p[ebase + e] = pbase + (key[r] & 127) * HW;
-            ent_iv[ebase + e] = __ldg(vox2iv + (key[r] >> 7));
+            ent_iv[ebase + e] = vox2iv ? __ldg(vox2iv + (key[r] >> 7)) : (key[r] >> 7);
         }
     }
 }

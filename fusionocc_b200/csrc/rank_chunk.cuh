@@ -286,7 +286,10 @@ static_assert(kChunkVox == 1024, "the kernels shift by 10");
 #ifndef FO_VOXCAM_MINB
 #define FO_VOXCAM_MINB 6
 #endif
-template <bool CALIB>
+// MODE: the matvec summation order (CalibArgs::mode) as a compile-time constant — with a run-time mode every one of
+// the nine 3-term dot products carried its own four-way branch (62 BRA, ~250 instructions per point; the kernel is
+// issue-bound).
+template <bool CALIB, int MODE>
 __global__ void __launch_bounds__(kChunkThreads, FO_VOXCAM_MINB) voxelize_count_cam_kernel(VoxArgs v, CalibArgs g, int n_cams,
                                                                                         int dhw) {
     constexpr int PPT = FO_VOXCAM_PPT;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kChunkThreads, FO_VOXCAM_MINB) voxelize_count_
         float x, y, z;
         if (CALIB) {
             const float *f = g.frustum + 3 * r;
-            calib_point_cam(cm, g.mode, g.bda_has_t != 0, __ldg(f), __ldg(f + 1), __ldg(f + 2), x, y, z);
+            calib_point_cam(cm, MODE, g.bda_has_t != 0, __ldg(f), __ldg(f + 1), __ldg(f + 2), x, y, z);
             if (g.coor_out) {
                 float *o = g.coor_out + 3 * (int64_t)p;
                 o[0] = x; o[1] = y; o[2] = z;

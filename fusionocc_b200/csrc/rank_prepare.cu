@@ -259,14 +259,16 @@ __global__ void __launch_bounds__(256) heavy_queue_kernel(const int32_t *__restr
 // row of a point is vox2iv[voxel].  No sort passes over memory, no atomics, fixed-stride rows of D entries.
 // ------------------------------------------------------------------------------------------------
 template <int R>   // R = ceil(D / 32) registers per lane; rank-by-counting on 64-bit (voxel, d) keys, D <= 256
-__global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t *__restrict__ pt2vox,
-                                                                  const int32_t *__restrict__ vox2iv, int D, int HW,
+__global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const FwdPlanHeader *fhdr,
+                                                                  const int32_t *__restrict__ pt2vox,
+                                                                  const int32_t *__restrict__ vox2iv_, int D, int HW,
                                                                   int n_rows, BwdPlanHeader *hdr, int32_t *ent_p,
                                                                   int32_t *ent_iv, int32_t *starts, int32_t *lengths,
                                                                   int32_t *ids, const int32_t *n_points_dev) {
     const int lane = threadIdx.x & 31;
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int32_t *vox2iv = plan_vox2iv(fhdr, vox2iv_);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
             if (key[r] != LLONG_MAX) {
                 const int64_t e = (int64_t)q * D + rank[r];
                 ent_p[e] = (bn * D + lane + 32 * r) * HW + hw;
-                ent_iv[e] = __ldg(vox2iv + (int)(key[r] >> 8));
+                ent_iv[e] = vox2iv ? __ldg(vox2iv + (int)(key[r] >> 8)) : (int)(key[r] >> 8);
                 ++cnt;
             }
         }
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_kernel(const int32_t 
 // Same job with a bitonic network over packed 32-bit keys (bwd_plan.cuh: plan_pixel_bitonic).
 template <int R>   // R in {1, 2, 4}: 32 * R >= D
 __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
-    const int32_t *__restrict__ pt2vox, const int32_t *__restrict__ vox2iv, int D, int HW, int n_rows,
+    const FwdPlanHeader *fhdr, const int32_t *__restrict__ pt2vox, const int32_t *__restrict__ vox2iv_, int D, int HW, int n_rows,
     BwdPlanHeader *hdr, int32_t *ent_p, int32_t *ent_iv, int32_t *starts, int32_t *lengths, int32_t *ids,
     const int32_t *n_points_dev) {
     __shared__ int s_cmp[8][32 * R];
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     int *cmp = s_cmp[threadIdx.x >> 5];
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int32_t *vox2iv = plan_vox2iv(fhdr, vox2iv_);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         hdr->n_bwd_intervals = n_rows;
         hdr->n_points = n_points_dev ? *n_points_dev : 0;
@@ -435,9 +438,9 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
 
 extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total) {
     if (n_points_total < 0 || n_voxels_total < 0) return 0;
-    // counters + aggregates | slot[P] | long-interval queue of the order pass [P/8 + 1]
+    // counters + aggregates | slot[P] | long-interval queue of the order pass [P/8 + 1] | (offset, interval) pairs [NV]
     const size_t legacy = bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256) +
-                          (size_t)align_up((n_points_total / 8 + 1) * 4, 256);
+                          (size_t)align_up((n_points_total / 8 + 1) * 4, 256) + (size_t)align_up(n_voxels_total * 8, 256);
     const size_t chunked = chunk_scratch_view(nullptr, chunk_bound(n_voxels_total), n_points_total).total_bytes;
     return legacy > chunked ? legacy : chunked;
 }
@@ -550,8 +553,14 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     if (vox_impl >= 1 && (int64_t)B * N <= 65535) {
         const int dhw = D * H * W, per = kChunkThreads * FO_VOXCAM_PPT;
         const dim3 grid_v((unsigned)((dhw + per - 1) / per), (unsigned)(B * N));
-        if (calib) FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw));
-        else FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<false>, grid_v, dim3(kChunkThreads), 0, stream, va, CalibArgs{}, N, dhw));
+        if (calib) {
+            switch (calib->mode) {
+                case 0: FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true, 0>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw)); break;
+                case 1: FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true, 1>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw)); break;
+                case 2: FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true, 2>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw)); break;
+                default: FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<true, 3>, grid_v, dim3(kChunkThreads), 0, stream, va, *calib, N, dhw)); break;
+            }
+        } else FO_CUDA(launch_pdl(kPdlRank, voxelize_count_cam_kernel<false, 0>, grid_v, dim3(kChunkThreads), 0, stream, va, CalibArgs{}, N, dhw));
     } else if (calib) FO_CUDA(launch_pdl(kPdlRank, voxelize_count_kernel<true>, dim3(grid_for((P + 3) / 4, 256)), dim3(256), 0, stream, va, *calib));
     else FO_CUDA(launch_pdl(kPdlRank, voxelize_count_kernel<false>, dim3(grid_for((P + 3) / 4, 256)), dim3(256), 0, stream, va, CalibArgs{}));
     FO_LAUNCH_CHECK("voxelize_count_kernel");
@@ -579,9 +588,18 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         ListArgs la;
         la.long_list = (int32_t *)((char *)slot + align_up(P * 4, 256)); la.long_cap = (int32_t)(P / 8 + 1);
         la.counts = ss.counter;
+        // FO_RANK_FAST=2 (opt-in): (offset, interval id) pairs + a placement that turns pt2vox into pt2iv, so that the
+        // backward plan needs no voxel -> interval gather.  Measured (profiles/r02_summary.md): backward -7 us, rank
+        // precompute +6 us at batch 8 (+19 / -16 us at 512x1408): a wash with a backward, a loss without one.
+        la.ofiv = fast >= 2 ? (int2 *)((char *)la.long_list + align_up(((int64_t)P / 8 + 1) * 4, 256)) : nullptr;
+        if (la.ofiv) sa.bucket2iv = nullptr;
         FO_CUDA(launch_pdl(kPdlRank, scan_buckets2_kernel, dim3(scan_blocks), dim3(kScan2Threads), 0, stream, sa, la));
-        FO_CUDA(launch_pdl(kPdlRank, place_kernel, dim3(grid_for(P, 256)), dim3(256), 0, stream, (const int32_t *)key,
-                           (const int32_t *)slot, (const int32_t *)ss.cnt, P, (const int32_t *)nullptr, NV, ranks_depth));
+        if (la.ofiv)
+            FO_CUDA(launch_pdl(kPdlRank, place_iv_kernel, dim3(grid_for((P + 3) / 4, 256)), dim3(256), 0, stream, key,
+                               (const int32_t *)slot, (const int2 *)la.ofiv, P, ranks_depth, pv.hdr));
+        else
+            FO_CUDA(launch_pdl(kPdlRank, place_kernel, dim3(grid_for(P, 256)), dim3(256), 0, stream, (const int32_t *)key,
+                               (const int32_t *)slot, (const int32_t *)ss.cnt, P, (const int32_t *)nullptr, NV, ranks_depth));
         Order2Args o2;
         o2.sorted = ranks_depth; o2.ranks_feat = ranks_feat; o2.ranks_bev = ranks_bev; o2.iv_starts = interval_starts;
         o2.iv_lengths = interval_lengths; o2.iv_bucket = pv.iv_vox; o2.n_intervals = counts_dev + 1;
@@ -737,7 +755,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
         const int blocks = grid_for(n_feat_rows * 32, 256, FO_PLAN_CTAS_PER_SM);
         if (D <= 128 && (int64_t)B * n_vox < (1 << 24)) {   // packed-key bitonic variant
 #define FO_BITONIC(RR)                                                                                          \
-    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2vox, fv.vox2iv, D, hw,             \
+    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.hdr, fv.pt2vox, fv.vox2iv, D, hw,             \
                                                                       (int)n_feat_rows, bv.hdr, bv.ent_p,      \
                                                                       bv.ent_iv, bv.starts, bv.lengths, bv.ids, \
                                                                       n_points_dev)
@@ -749,7 +767,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
             return FO_OK;
         }
 #define FO_STRUCT(RR)                                                                                         \
-    bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.pt2vox, fv.vox2iv, D, hw, (int)n_feat_rows, \
+    bwd_plan_structured_kernel<RR><<<blocks, 256, 0, stream>>>(fv.hdr, fv.pt2vox, fv.vox2iv, D, hw, (int)n_feat_rows, \
                                                               bv.hdr, bv.ent_p, bv.ent_iv, bv.starts,        \
                                                               bv.lengths, bv.ids, n_points_dev)
         switch (R) {
