@@ -49,7 +49,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 6 + 1 + 2         # rank_prepare, forward, backward: TMA gather with the plan CTAs + pixel kernel
+KERNELS_PER_STEP = 6 + 1 + 3         # rank_prepare (zero, voxelise, tile sums, scan, place, order), forward, backward (zero, TMA gather with the plan CTAs, pixel kernel)
                                      # (memsets not counted)
 
 

@@ -548,6 +548,7 @@ struct PlanRideArgs {
     const int32_t *pt2vox, *vox2iv;
     int32_t D, HW, n_rows;
     int32_t n_plan_ctas, n_gather_ctas, gu;   // gu = gather CTAs per sample
+    int32_t plan_first;                       // 1: the plan CTAs are the first blocks of the grid instead of interleaved
     BwdPlanHeader *hdr;
     int32_t *ent_p, *ent_iv, *starts, *lengths, *ids;
     const int32_t *n_points_dev;
@@ -565,8 +566,8 @@ __global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, P
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long T = (long long)p.n_plan_ctas + p.n_gather_ctas;
     const int bid = blockIdx.x;
-    const int plans_before = (int)(((long long)bid * p.n_plan_ctas) / T);
-    const bool is_plan = (int)(((long long)(bid + 1) * p.n_plan_ctas) / T) > plans_before;
+    const int plans_before = p.plan_first ? min(bid, p.n_plan_ctas) : (int)(((long long)bid * p.n_plan_ctas) / T);
+    const bool is_plan = p.plan_first ? bid < p.n_plan_ctas : (int)(((long long)(bid + 1) * p.n_plan_ctas) / T) > plans_before;
     if (is_plan) {
         if (plans_before == 0 && threadIdx.x == 0) {
             p.hdr->n_bwd_intervals = p.n_rows;
@@ -746,10 +747,13 @@ int bwd_impl_choice() {
     return (e && *e) ? atoi(e) : 1;
 }
 
-// FO_BWD_RIDE=0 (A/B): build a requested plan as its own launch instead of inside the gather kernel
-bool bwd_ride_choice() {
+// FO_BWD_RIDE (A/B): 0 = build a requested plan as its own launch, 1 = plan CTAs interleaved with the gather CTAs,
+// 2 = plan CTAs first in the gather grid; default (-1): by shape — first when the plan is small against the gather
+// (few pixels per sub-tile: 405.9 -> 400.9 us per step at the headline shape, 83.6 -> 77.5 us at batch 1), interleaved
+// otherwise (512x1408: 943.7 us interleaved, 951.7 first, 960.8 as a launch of its own)
+int bwd_ride_choice() {
     const char *e = getenv("FO_BWD_RIDE");
-    return !(e && *e) || atoi(e) != 0;
+    return (e && *e) ? atoi(e) : -1;
 }
 
 int launch_pixel2(const PixelArgs &pa, cudaStream_t stream) {
@@ -866,12 +870,14 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
                                   n_feat_rows % req->hw == 0 && n_depth == n_feat_rows * D && n_depth <= pv.p_cap &&
                                   bv.cap >= n_depth && (int64_t)gu * B + n_feat_rows / 16 + 1 < INT_MAX &&
                                   g_smem <= 48 * 1024 &&      // wide channel counts leave two gather CTAs per SM: no room to share
-                                  bwd_ride_choice();
+                                  bwd_ride_choice() != 0;
                 if (ride) {
                     PlanRideArgs pr;
                     pr.fhdr = pv.hdr; pr.pt2vox = pv.pt2vox; pr.vox2iv = pv.vox2iv; pr.D = D; pr.HW = req->hw; pr.n_rows = (int)n_feat_rows;
                     pr.gu = gu; pr.n_gather_ctas = gu * B;
                     pr.n_plan_ctas = (int)((n_feat_rows + 8 * kPlanPixPerWarp - 1) / (8 * kPlanPixPerWarp));
+                    const int ride = bwd_ride_choice();
+                    pr.plan_first = ride == 2 || (ride < 0 && (int64_t)pr.n_plan_ctas * 6 <= pr.n_gather_ctas) ? 1 : 0;
                     pr.hdr = bv.hdr; pr.ent_p = bv.ent_p; pr.ent_iv = bv.ent_iv; pr.starts = bv.starts;
                     pr.lengths = bv.lengths; pr.ids = bv.ids; pr.n_points_dev = req->n_points_dev;
                     const int R = D <= 32 ? 1 : (D <= 64 ? 2 : 4);

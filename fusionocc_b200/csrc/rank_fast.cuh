@@ -86,32 +86,61 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
     const int ne0 = (int)(tile_prefix & 0xffffffffu);          // first interval of this tile
     const int n_tile = (int)(tile_total & 0xffffffffu);        // intervals of this tile
 
-    int64_t vin = 0, sample = 0;
     const bool want_tiles = a.sub_iv != nullptr;
-    if (want_tiles) { sample = base / a.vox_per_sample; vin = base - sample * a.vox_per_sample; }
-
     int o[kScan2Items], iv[kScan2Items];
-#pragma unroll
-    for (int j = 0; j < kScan2Items; ++j) {
-        const int64_t v = base + j;
-        o[j] = (int)pts;
-        iv[j] = (int)ne;
-        if (v < a.n_buckets) {
-            if (want_tiles) {
-                if ((vin & (kSub - 1)) == 0) {
-                    const int64_t u = sample * a.subs_per_sample + (vin >> kSubShift);
-                    a.sub_iv[u] = (int)ne;
-                    a.sub_pt[u] = (int)pts;
-                }
-                if (++vin == a.vox_per_sample) { vin = 0; ++sample; }
+    // fast path (every tile but a ragged last one, voxels per sample a multiple of 8): the thread's eight buckets lie in
+    // one sample, a sub-tile can only start at its first bucket, all indices fit 32 bits
+    const bool fast = (int64_t)(tile + 1) * kScanTile <= a.n_buckets && (a.vox_per_sample & 7) == 0 &&
+                      a.n_buckets < (int64_t)INT_MAX;
+    if (fast) {
+        const int b32 = (int)base;
+        if (want_tiles) {
+            const int sample = b32 / (int)a.vox_per_sample, vin = b32 - sample * (int)a.vox_per_sample;
+            if ((vin & (kSub - 1)) == 0) {
+                const int u = sample * a.subs_per_sample + (vin >> kSubShift);
+                a.sub_iv[u] = (int)ne;
+                a.sub_pt[u] = (int)pts;
             }
+        }
+        int li = (int)ne - ne0;
+#pragma unroll
+        for (int j = 0; j < kScan2Items; ++j) {
+            o[j] = (int)pts;
+            iv[j] = ne0 + li;
             if (c[j] > 0) {
-                const int li = (int)ne - ne0;
                 s_st[li] = (int)pts;
                 s_ln[li] = c[j];
-                s_vx[li] = (int)v;
+                s_vx[li] = b32 + j;
                 pts += (unsigned)c[j];
-                ++ne;
+                ++li;
+            }
+        }
+        ne = (unsigned)(ne0 + li);
+    } else {
+        int64_t vin = 0, sample = 0;
+        if (want_tiles) { sample = base / a.vox_per_sample; vin = base - sample * a.vox_per_sample; }
+#pragma unroll
+        for (int j = 0; j < kScan2Items; ++j) {
+            const int64_t v = base + j;
+            o[j] = (int)pts;
+            iv[j] = (int)ne;
+            if (v < a.n_buckets) {
+                if (want_tiles) {
+                    if ((vin & (kSub - 1)) == 0) {
+                        const int64_t u = sample * a.subs_per_sample + (vin >> kSubShift);
+                        a.sub_iv[u] = (int)ne;
+                        a.sub_pt[u] = (int)pts;
+                    }
+                    if (++vin == a.vox_per_sample) { vin = 0; ++sample; }
+                }
+                if (c[j] > 0) {
+                    const int li = (int)ne - ne0;
+                    s_st[li] = (int)pts;
+                    s_ln[li] = c[j];
+                    s_vx[li] = (int)v;
+                    pts += (unsigned)c[j];
+                    ++ne;
+                }
             }
         }
     }

@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(256) bwd_plan_structured_bitonic_kernel(
     BwdPlanHeader *hdr, int32_t *ent_p, int32_t *ent_iv, int32_t *starts, int32_t *lengths, int32_t *ids,
     const int32_t *n_points_dev) {
     __shared__ int s_cmp[8][32 * R];
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31;
     int *cmp = s_cmp[threadIdx.x >> 5];
     const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -755,10 +757,10 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
         const int blocks = grid_for(n_feat_rows * 32, 256, FO_PLAN_CTAS_PER_SM);
         if (D <= 128 && (int64_t)B * n_vox < (1 << 24)) {   // packed-key bitonic variant
 #define FO_BITONIC(RR)                                                                                          \
-    bwd_plan_structured_bitonic_kernel<RR><<<blocks, 256, 0, stream>>>(fv.hdr, fv.pt2vox, fv.vox2iv, D, hw,             \
-                                                                      (int)n_feat_rows, bv.hdr, bv.ent_p,      \
-                                                                      bv.ent_iv, bv.starts, bv.lengths, bv.ids, \
-                                                                      n_points_dev)
+    FO_CUDA(launch_pdl(kPdlGather, bwd_plan_structured_bitonic_kernel<RR>, dim3(blocks), dim3(256), 0, stream,   \
+                       (const FwdPlanHeader *)fv.hdr, (const int32_t *)fv.pt2vox, (const int32_t *)fv.vox2iv, D, \
+                       (int)hw, (int)n_feat_rows, bv.hdr, bv.ent_p, bv.ent_iv, bv.starts, bv.lengths, bv.ids,   \
+                       n_points_dev))
             if (R == 1) FO_BITONIC(1);
             else if (R == 2) FO_BITONIC(2);
             else FO_BITONIC(4);
