@@ -554,16 +554,20 @@ struct PlanRideArgs {
     const int32_t *n_points_dev;
 };
 constexpr int kPlanPixPerWarp = 2;
+#ifndef FO_GRIDE_MINB
+#define FO_GRIDE_MINB 6      // 40 registers; plan CTAs sort in the stage area, so six CTAs fit the SM's shared memory
+#endif
 
 template <int NACC, bool EXACT, int R>
-__global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, PlanRideArgs p,
+__global__ void __launch_bounds__(256, FO_GRIDE_MINB) bwd_gather_plan_kernel(GatherArgs a, PlanRideArgs p,
                                                                  const __grid_constant__ CUtensorMap tm) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ __align__(8) unsigned long long s_bar[8];
-    __shared__ int s_cmp[8][32 * R];
     pdl_wait();
     pdl_launch();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // a plan CTA sorts in the (otherwise unused) stage area: one kind of shared memory per CTA, six CTAs per SM
+    int *s_cmp = reinterpret_cast<int *>(gsm) + warp * (32 * R);
     const long long T = (long long)p.n_plan_ctas + p.n_gather_ctas;
     const int bid = blockIdx.x;
     const int plans_before = p.plan_first ? min(bid, p.n_plan_ctas) : (int)(((long long)bid * p.n_plan_ctas) / T);
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(256, 5) bwd_gather_plan_kernel(GatherArgs a, P
         const int32_t *v2i = plan_vox2iv(p.fhdr, p.vox2iv);
 #pragma unroll 1
         for (int q = q0; q < min(p.n_rows, q0 + kPlanPixPerWarp); ++q)
-            plan_pixel_bitonic<R>(p.pt2vox, v2i, p.D, p.HW, q, s_cmp[warp], lane, p.ent_p, p.ent_iv, p.starts,
+            plan_pixel_bitonic<R>(p.pt2vox, v2i, p.D, p.HW, q, s_cmp, lane, p.ent_p, p.ent_iv, p.starts,
                                   p.lengths, p.ids);
         return;
     }
@@ -748,9 +752,9 @@ int bwd_impl_choice() {
 }
 
 // FO_BWD_RIDE (A/B): 0 = build a requested plan as its own launch, 1 = plan CTAs interleaved with the gather CTAs,
-// 2 = plan CTAs first in the gather grid; default (-1): by shape — first when the plan is small against the gather
-// (few pixels per sub-tile: 405.9 -> 400.9 us per step at the headline shape, 83.6 -> 77.5 us at batch 1), interleaved
-// otherwise (512x1408: 943.7 us interleaved, 951.7 first, 960.8 as a launch of its own)
+// 2 = plan CTAs first in the gather grid; default (-1): first for short gather grids (up to 8 waves of resident CTAs:
+// 82.7 -> 76.5 us per step at batch 1, 128.5 -> 122.1 us at batch 2), interleaved for long ones (batch 8: 398.2 us
+// interleaved, 401.9 first; 512x1408: 931.9 / 955.1)
 int bwd_ride_choice() {
     const char *e = getenv("FO_BWD_RIDE");
     return (e && *e) ? atoi(e) : -1;
@@ -877,7 +881,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
                     pr.gu = gu; pr.n_gather_ctas = gu * B;
                     pr.n_plan_ctas = (int)((n_feat_rows + 8 * kPlanPixPerWarp - 1) / (8 * kPlanPixPerWarp));
                     const int ride = bwd_ride_choice();
-                    pr.plan_first = ride == 2 || (ride < 0 && (int64_t)pr.n_plan_ctas * 6 <= pr.n_gather_ctas) ? 1 : 0;
+                    pr.plan_first = ride == 2 || (ride < 0 && pr.n_gather_ctas <= 8 * FO_GRIDE_MINB * sm_count()) ? 1 : 0;
                     pr.hdr = bv.hdr; pr.ent_p = bv.ent_p; pr.ent_iv = bv.ent_iv; pr.starts = bv.starts;
                     pr.lengths = bv.lengths; pr.ids = bv.ids; pr.n_points_dev = req->n_points_dev;
                     const int R = D <= 32 ? 1 : (D <= 64 ? 2 : 4);
