@@ -30,6 +30,7 @@ struct GatherArgs {
     const FwdPlanHeader *hdr;
     const int32_t *sub_iv;
     const int32_t *iv_vox;
+    const uint8_t *sub_occ;         // half-occupancy bits per sub-tile (nullptr: always fetch the whole sub-tile)
     float *G;                       // [n_intervals, C]
 };
 
@@ -474,20 +475,29 @@ __global__ void __launch_bounds__(kPix2Threads, FO_PIX2_MINB) bwd_pixel2_kernel(
 // Split in two so that a warp can have the boxes of several sub-tiles in flight before it consumes the first.
 struct GatherTile {
     int ia, ni, my_v;
+    int half;                       // 0: whole sub-tile staged (128-byte rows); 1 / 2: only its lower / upper 16 voxels (64-byte rows)
 };
 template <int NACC, bool EXACT>
-__device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensorMap *tm, float *stage, const unsigned bar,
-                                             const int b, const int su, const int lane, GatherTile &t) {
+__device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensorMap *tm, const CUtensorMap *tmh, float *stage,
+                                             const unsigned bar, const int b, const int su, const int lane, GatherTile &t) {
     const int C = EXACT ? 32 * NACC : a.C;
     t.ni = 0;
     if (su >= a.sps) return false;
     const int u = b * a.sps + su;
     const int ia = __ldg(a.sub_iv + u), ib = __ldg(a.sub_iv + u + 1);
+    const int occ = a.sub_occ ? (int)__ldg(a.sub_occ + u) : 3;
     if (ib <= ia) return false;
     const int v0 = su << kSubShift;
+    // a sub-tile with only one occupied 16-voxel half: fetch 64-byte rows (what the memory system fetches at least)
+    t.half = (occ == 1 || occ == 2) ? occ : 0;
     if (lane == 0) {
-        mbar_expect_tx(bar, (unsigned)C * 128u);
-        tma_load_3d((unsigned)__cvta_generic_to_shared(stage), tm, v0, 0, b, bar);
+        if (t.half) {
+            mbar_expect_tx(bar, (unsigned)C * 64u);
+            tma_load_3d((unsigned)__cvta_generic_to_shared(stage), tmh, v0 + (t.half == 2 ? kSub / 2 : 0), 0, b, bar);
+        } else {
+            mbar_expect_tx(bar, (unsigned)C * 128u);
+            tma_load_3d((unsigned)__cvta_generic_to_shared(stage), tm, v0, 0, b, bar);
+        }
     }
     const int nv = (int)min((int64_t)kSub, a.V - v0);
     const int vbase = (int)((int64_t)b * a.V) + v0;
@@ -507,6 +517,17 @@ __device__ __forceinline__ void gather_emit(const GatherArgs &a, const float *st
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
     float *dst = a.G + (int64_t)t.ia * C + lane;
     mbar_wait(bar, parity);
+    if (t.half) {
+        const int vlo = t.half == 2 ? kSub / 2 : 0;
+        for (int l = 0; l < t.ni; ++l, dst += C) {
+            const int v = __shfl_sync(0xffffffffu, t.my_v, l) - vlo;
+            if ((unsigned)v >= (unsigned)(kSub / 2)) continue;       // warp-uniform (a voxel outside the staged half: never for a consistent plan)
+#pragma unroll
+            for (int k = 0; k < NACC; ++k)
+                if (EXACT || lane + 32 * k < C) dst[32 * k] = lds_f32(sbase + swz64_off(lane + 32 * k, v));
+        }
+        return;
+    }
     for (int l = 0; l < t.ni; ++l, dst += C) {
         const int v = __shfl_sync(0xffffffffu, t.my_v, l);
         if (v < 0) continue;                         // warp-uniform
@@ -517,7 +538,8 @@ __device__ __forceinline__ void gather_emit(const GatherArgs &a, const float *st
 }
 
 template <int NACC, bool EXACT>
-__global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const __grid_constant__ CUtensorMap tm) {
+__global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const __grid_constant__ CUtensorMap tm,
+                                                             const __grid_constant__ CUtensorMap tmh) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ __align__(8) unsigned long long s_bar[8];
     pdl_wait();
@@ -532,7 +554,7 @@ __global__ void __launch_bounds__(256) bwd_gather_tma_kernel(GatherArgs a, const
     __syncwarp();
     float *stage = reinterpret_cast<float *>(base + warp * stage_bytes);
     GatherTile t;
-    if (gather_issue<NACC, EXACT>(a, &tm, stage, bar, blockIdx.y, blockIdx.x * 8 + warp, lane, t))
+    if (gather_issue<NACC, EXACT>(a, &tm, &tmh, stage, bar, blockIdx.y, blockIdx.x * 8 + warp, lane, t))
         gather_emit<NACC, EXACT>(a, stage, bar, 0, lane, t);
 }
 
@@ -560,7 +582,8 @@ constexpr int kPlanPixPerWarp = 2;
 
 template <int NACC, bool EXACT, int R>
 __global__ void __launch_bounds__(256, FO_GRIDE_MINB) bwd_gather_plan_kernel(GatherArgs a, PlanRideArgs p,
-                                                                 const __grid_constant__ CUtensorMap tm) {
+                                                                 const __grid_constant__ CUtensorMap tm,
+                                                                 const __grid_constant__ CUtensorMap tmh) {
     extern __shared__ __align__(1024) unsigned char gsm[];
     __shared__ __align__(8) unsigned long long s_bar[8];
     pdl_wait();
@@ -596,7 +619,7 @@ __global__ void __launch_bounds__(256, FO_GRIDE_MINB) bwd_gather_plan_kernel(Gat
     __syncwarp();
     float *stage = reinterpret_cast<float *>(base + warp * stage_bytes);
     GatherTile t;
-    if (gather_issue<NACC, EXACT>(a, &tm, stage, bar, b, blk * 8 + warp, lane, t))
+    if (gather_issue<NACC, EXACT>(a, &tm, &tmh, stage, bar, b, blk * 8 + warp, lane, t))
         gather_emit<NACC, EXACT>(a, stage, bar, 0, lane, t);
 }
 
@@ -849,7 +872,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         GatherArgs ga;
         ga.og = out_grad + (int64_t)c_offset * n_vox; ga.og_bstride = (int64_t)c_total * n_vox; ga.C = c; ga.V = n_vox;
         ga.sps = sps;
-        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.G = G;
+        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.sub_occ = pv.sub_occ; ga.G = G;
         pa.G = G; pa.row_map = nullptr; pa.n_rows_G = n_intervals; pa.g_rowstride = c;
         if (c > 256 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "channel or batch count too large for the gather kernel");
         // plans built from caller-supplied intervals may be flagged non-canonical on the device: the per-interval
@@ -861,8 +884,14 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         }
         const bool tma = v2_ok && n_intervals * c < INT_MAX && tmap_ok(ga.og, n_vox, c, c_total);
         if (tma) {
-            CUtensorMap tm;
+            CUtensorMap tm, tmh;
             if (int rc = make_voxel_tmap(&tm, ga.og, n_vox, c, c_total, B)) return rc;
+            if (int rc = make_voxel_tmap(&tmh, ga.og, n_vox, c, c_total, B, true)) return rc;
+            // FO_BWD_HALF=0 (A/B): always fetch whole sub-tiles
+            {
+                const char *he = getenv("FO_BWD_HALF");
+                if (he && *he && atoi(he) == 0) ga.sub_occ = nullptr;
+            }
             const int nacc = (c + 31) / 32;
             const bool exact = c % 32 == 0;
             const size_t stage_bytes = ((size_t)c * 128 + 1023) & ~(size_t)1023;
@@ -891,7 +920,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
             FO_CUDA(cudaFuncSetAttribute(bwd_gather_plan_kernel<NA, EX, RR>,                                          \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem));                  \
         FO_CUDA(launch_pdl(kPdlGather, bwd_gather_plan_kernel<NA, EX, RR>, dim3((unsigned)(pr.n_gather_ctas + pr.n_plan_ctas)),   \
-                           dim3(256), g_smem, stream, ga, pr, tm));                                                   \
+                           dim3(256), g_smem, stream, ga, pr, tm, tmh));                                                   \
     } while (0)
 #define FO_GRIDE_R(NA, EX)                                                                                            \
     do {                                                                                                              \
@@ -914,7 +943,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         if (g_smem > 48 * 1024)                                                                                    \
             FO_CUDA(cudaFuncSetAttribute(bwd_gather_tma_kernel<NA, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)g_smem));                                                            \
-        FO_CUDA(launch_pdl(kPdlGather, bwd_gather_tma_kernel<NA, EX>, dim3(gu, B), dim3(256), g_smem, stream, ga, tm));        \
+        FO_CUDA(launch_pdl(kPdlGather, bwd_gather_tma_kernel<NA, EX>, dim3(gu, B), dim3(256), g_smem, stream, ga, tm, tmh));        \
     } while (0)
                 if (nacc == 1) { if (exact) FO_GTMA(1, true); else FO_GTMA(1, false); }
                 else if (nacc == 2) { if (exact) FO_GTMA(2, true); else FO_GTMA(2, false); }

@@ -74,10 +74,15 @@ __host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vo
 
 // ----------------------------------------------------------------------------------------------
 // Forward plan buffer:
-//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | vox2iv[NV] | pos2iv[P_cap] | pt2vox[P_cap] | iv_vox[IV_cap]]
+//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | sub_occ[bound+1] (bytes) | vox2iv[NV] | pos2iv[P_cap] |
+//    pt2vox[P_cap] | iv_vox[IV_cap]]
 //   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
 //   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
 //   heavy_list[]  the dense sub-tiles (more than kHeavyPts points), in no particular order
+//   sub_occ[u]    bit 0 / bit 1: the lower / upper 16 voxels of sub-tile u may hold an occupied voxel (3 = unknown:
+//                 treat both as occupied).  The backward's gather fetches only the occupied 64-byte halves of the
+//                 out_grad rows of a sub-tile — 64 bytes is what the memory system fetches at least
+//                 (profiles/micro/sector_gran.cu).
 //   vox2iv[v]     interval id of voxel v (rows of the backward's gathered out_grad); only when hdr.structured
 //   pos2iv[i]     interval id of sorted position i; only for plans built from caller-supplied intervals
 //   pt2vox[p]     voxel id of frustum point p, -1 if filtered; only when hdr.structured
@@ -92,6 +97,7 @@ struct FwdPlanView {
     int32_t *sub_iv;
     int32_t *sub_pt;
     int32_t *heavy_list;
+    uint8_t *sub_occ;
     int32_t *vox2iv;
     int32_t *pos2iv;
     int32_t *iv_vox;
@@ -103,15 +109,19 @@ __host__ inline int64_t fwd_plan_subs_bound(int64_t n_vox_total) { return n_vox_
 __host__ inline size_t fwd_plan_sub_bytes(int64_t n_vox_total) {
     return (size_t)align_up((fwd_plan_subs_bound(n_vox_total) + 1) * 4, 256);
 }
+__host__ inline size_t fwd_plan_occ_bytes(int64_t n_vox_total) {
+    return (size_t)align_up(fwd_plan_subs_bound(n_vox_total) + 1, 256);
+}
 __host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
     const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
-    return 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv + 8 * pc + 4 * (pc < nv ? pc : nv));
+    return 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + fwd_plan_occ_bytes(n_vox_total) +
+           (size_t)(4 * nv + 8 * pc + 4 * (pc < nv ? pc : nv));
 }
 // The layout is a pure function of (n_vox_total, plan_bytes): every entry point is handed the same
 // plan_bytes the buffer was sized with and recovers the same pointers without reading the device.
 __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_bytes, FwdPlanView *v) {
     const int64_t nv = align_up(n_vox_total, 64);
-    const size_t fixed = 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + (size_t)(4 * nv);
+    const size_t fixed = 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + fwd_plan_occ_bytes(n_vox_total) + (size_t)(4 * nv);
     if (plan_bytes < fixed + 64 * 12) return false;
     const int64_t rest = (int64_t)(plan_bytes - fixed);
     int64_t pc = rest / 12;
@@ -122,6 +132,7 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
     v->sub_iv = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->sub_pt = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->heavy_list = (int32_t *)p;            p += fwd_plan_sub_bytes(n_vox_total);
+    v->sub_occ = (uint8_t *)p;               p += fwd_plan_occ_bytes(n_vox_total);
     v->vox2iv = (int32_t *)p;                p += nv * 4;
     v->pos2iv = (int32_t *)p;                p += pc * 4;
     v->pt2vox = (int32_t *)p;                p += pc * 4;

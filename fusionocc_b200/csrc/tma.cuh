@@ -43,15 +43,19 @@ inline bool tmap_ok(const void *base, int64_t V, int32_t C, int32_t c_total) {
            (int64_t)c_total * V * 4 < (1ll << 40);
 }
 
-inline int make_voxel_tmap(CUtensorMap *tm, const float *base, int64_t V, int32_t C, int32_t c_total, int32_t B) {
+// half = false: box of a whole sub-tile (32 voxels = 128-byte rows, 128-byte swizzle);
+// half = true:  box of half a sub-tile (16 voxels = 64-byte rows, 64-byte swizzle) — the gather's sparse sub-tiles
+inline int make_voxel_tmap(CUtensorMap *tm, const float *base, int64_t V, int32_t C, int32_t c_total, int32_t B,
+                           bool half = false) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return set_error(FO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t gdim[3] = {(cuuint64_t)V, (cuuint64_t)C, (cuuint64_t)B};
     const cuuint64_t gstr[2] = {(cuuint64_t)V * 4, (cuuint64_t)c_total * V * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kSub, (cuuint32_t)C, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(half ? kSub / 2 : kSub), (cuuint32_t)C, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           half ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FO_OK;
@@ -64,6 +68,11 @@ inline int make_voxel_tmap(CUtensorMap *tm, const float *base, int64_t V, int32_
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned swz_off(int c, int v) {
     return ((unsigned)c << 7) + ((((unsigned)v >> 2) ^ ((unsigned)c & 7u)) << 4) + (((unsigned)v & 3u) << 2);
+}
+
+// Half box (16 voxels, 64-byte rows, 64-byte swizzle: address bits [5:4] ^= bits [8:7]): element (c, v), v < 16
+__device__ __forceinline__ unsigned swz64_off(int c, int v) {
+    return ((unsigned)c << 6) + ((((unsigned)v >> 2) ^ (((unsigned)c >> 1) & 3u)) << 4) + (((unsigned)v & 3u) << 2);
 }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
