@@ -290,7 +290,10 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
 //     73 % of the stall cycles on the copies' scoreboard, 1.3 TB/s.  And an upper bound for moving depth_grad out of
 //     this kernel: with the tile stores and the depth-grad chains compiled OUT the kernel is no
 //     faster (backward 197.7 vs 192.3 us, 72 registers, 4 or 6 CTAs per SM) — its time is the two dependent index
-//     round trips and the scattered 128-byte row reads, not the chains.
+//     round trips and the scattered 128-byte row reads, not the chains.  Nor is it bytes in flight: a second register
+//     set holding the rows of the tile after next (16 rows in flight per lane, 143 registers, 14 warps per SM) made it
+//     SLOWER, 182.3 -> 189.9 us per backward (405 -> 446 us at 512x1408); ncu of the shipped kernel: L1/TEX throughput
+//     72 %, DRAM 42 %, 14 warps per SM, first use of a tile's rows = 38 % of the stall samples.
 // (4) NOT KEPT: one fused launch (gather units of sample b+1 interleaved with pixel units of sample b, device-side
 //     completion counters, G consumed while L2-resident).  Measured on a B200 at the headline shape, batch 8
 //     (profiles/r02_summary.md): two launches 163 us; fused and interleaved 225 us, with a two-stage box ring per
