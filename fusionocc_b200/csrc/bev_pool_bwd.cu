@@ -30,7 +30,7 @@ struct GatherArgs {
     const FwdPlanHeader *hdr;
     const int32_t *sub_iv;
     const int32_t *iv_vox;
-    const uint8_t *sub_occ;         // half-occupancy bits per sub-tile (nullptr: always fetch the whole sub-tile)
+    const uint32_t *sub_mask;       // occupancy mask per sub-tile (nullptr / 0: unknown — read iv_vox, fetch the whole sub-tile)
     float *G;                       // [n_intervals, C]
 };
 
@@ -488,11 +488,11 @@ __device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensor
     if (su >= a.sps) return false;
     const int u = b * a.sps + su;
     const int ia = __ldg(a.sub_iv + u), ib = __ldg(a.sub_iv + u + 1);
-    const int occ = a.sub_occ ? (int)__ldg(a.sub_occ + u) : 3;
+    const unsigned mask = a.sub_mask ? __ldg(a.sub_mask + u) : 0u;
     if (ib <= ia) return false;
     const int v0 = su << kSubShift;
     // a sub-tile with only one occupied 16-voxel half: fetch 64-byte rows (what the memory system fetches at least)
-    t.half = (occ == 1 || occ == 2) ? occ : 0;
+    t.half = mask == 0u ? 0 : ((mask >> 16) == 0u ? 1 : ((mask & 0xFFFFu) == 0u ? 2 : 0));
     if (lane == 0) {
         if (t.half) {
             mbar_expect_tx(bar, (unsigned)C * 64u);
@@ -503,11 +503,15 @@ __device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensor
         }
     }
     const int nv = (int)min((int64_t)kSub, a.V - v0);
-    const int vbase = (int)((int64_t)b * a.V) + v0;
     t.ia = ia;
     t.ni = min(ib - ia, kSub);
     t.my_v = -1;
-    if (lane < t.ni) {
+    if (mask != 0u) {
+        // interval l of the sub-tile is the l-th occupied voxel: no second, dependent index load
+        if (lane < t.ni) t.my_v = (int)__fns(mask, 0u, lane + 1);
+        if ((unsigned)t.my_v >= (unsigned)nv) t.my_v = -1;
+    } else if (lane < t.ni) {
+        const int vbase = (int)((int64_t)b * a.V) + v0;
         t.my_v = __ldg(a.iv_vox + ia + lane) - vbase;
         if ((unsigned)t.my_v >= (unsigned)nv) t.my_v = -1;
     }
@@ -875,7 +879,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
         GatherArgs ga;
         ga.og = out_grad + (int64_t)c_offset * n_vox; ga.og_bstride = (int64_t)c_total * n_vox; ga.C = c; ga.V = n_vox;
         ga.sps = sps;
-        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.sub_occ = pv.sub_occ; ga.G = G;
+        ga.hdr = pv.hdr; ga.sub_iv = pv.sub_iv; ga.iv_vox = pv.iv_vox; ga.sub_mask = pv.sub_mask; ga.G = G;
         pa.G = G; pa.row_map = nullptr; pa.n_rows_G = n_intervals; pa.g_rowstride = c;
         if (c > 256 || B > 65535) return set_error(FO_ERR_UNSUPPORTED, "channel or batch count too large for the gather kernel");
         // plans built from caller-supplied intervals may be flagged non-canonical on the device: the per-interval
@@ -893,7 +897,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
             // FO_BWD_HALF=0 (A/B): always fetch whole sub-tiles
             {
                 const char *he = getenv("FO_BWD_HALF");
-                if (he && *he && atoi(he) == 0) ga.sub_occ = nullptr;
+                if (he && *he && atoi(he) == 0) ga.sub_mask = nullptr;
             }
             const int nacc = (c + 31) / 32;
             const bool exact = c % 32 == 0;

@@ -83,7 +83,7 @@ struct ScanArgs {
     // forward flavour: first interval / first point of every 32-voxel sub-tile (nullptr to skip)
     int32_t *sub_iv;
     int32_t *sub_pt;
-    uint8_t *sub_occ;        // optional: half-occupancy bits of every sub-tile (written by scan_buckets2_kernel only)
+    uint32_t *sub_mask;      // optional: occupancy mask of every sub-tile (written by scan_buckets2_kernel only)
     int64_t  vox_per_sample;
     int32_t  subs_per_sample;
     int32_t  n_subs;

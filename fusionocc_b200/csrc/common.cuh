@@ -74,14 +74,15 @@ __host__ __device__ inline int64_t subs_per_sample(int64_t n_vox) { return (n_vo
 
 // ----------------------------------------------------------------------------------------------
 // Forward plan buffer:
-//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | sub_occ[bound+1] (bytes) | vox2iv[NV] | pos2iv[P_cap] |
+//   [header(256) | sub_iv[bound+1] | sub_pt[bound+1] | heavy_list[bound+1] | sub_mask[bound+1] | vox2iv[NV] | pos2iv[P_cap] |
 //    pt2vox[P_cap] | iv_vox[IV_cap]]
 //   sub_iv[u]     first interval whose voxel lies in sub-tile u          (sub_iv[n_sub] = n_intervals)
 //   sub_pt[u]     sorted position of that interval's first point         (sub_pt[n_sub] = end of points)
 //   heavy_list[]  the dense sub-tiles (more than kHeavyPts points), in no particular order
-//   sub_occ[u]    bit 0 / bit 1: the lower / upper 16 voxels of sub-tile u may hold an occupied voxel (3 = unknown:
-//                 treat both as occupied).  The backward's gather fetches only the occupied 64-byte halves of the
-//                 out_grad rows of a sub-tile — 64 bytes is what the memory system fetches at least
+//   sub_mask[u]   bit v set: voxel v of sub-tile u is occupied (0 = unknown: the reader falls back to iv_vox).  The
+//                 backward's gather gets its interval -> voxel map from this word (interval l of the sub-tile is its
+//                 l-th set bit) instead of a second, dependent load of iv_vox, and fetches only the occupied 64-byte
+//                 halves of the out_grad rows — 64 bytes is what the memory system fetches at least
 //                 (profiles/micro/sector_gran.cu).
 //   vox2iv[v]     interval id of voxel v (rows of the backward's gathered out_grad); only when hdr.structured
 //   pos2iv[i]     interval id of sorted position i; only for plans built from caller-supplied intervals
@@ -97,7 +98,7 @@ struct FwdPlanView {
     int32_t *sub_iv;
     int32_t *sub_pt;
     int32_t *heavy_list;
-    uint8_t *sub_occ;
+    uint32_t *sub_mask;
     int32_t *vox2iv;
     int32_t *pos2iv;
     int32_t *iv_vox;
@@ -109,9 +110,7 @@ __host__ inline int64_t fwd_plan_subs_bound(int64_t n_vox_total) { return n_vox_
 __host__ inline size_t fwd_plan_sub_bytes(int64_t n_vox_total) {
     return (size_t)align_up((fwd_plan_subs_bound(n_vox_total) + 1) * 4, 256);
 }
-__host__ inline size_t fwd_plan_occ_bytes(int64_t n_vox_total) {
-    return (size_t)align_up(fwd_plan_subs_bound(n_vox_total) + 1, 256);
-}
+__host__ inline size_t fwd_plan_occ_bytes(int64_t n_vox_total) { return fwd_plan_sub_bytes(n_vox_total); }
 __host__ inline size_t fwd_plan_bytes_for(int64_t n_vox_total, int64_t p_cap) {
     const int64_t pc = align_up(p_cap > 0 ? p_cap : 1, 64), nv = align_up(n_vox_total, 64);
     return 256 + 3 * fwd_plan_sub_bytes(n_vox_total) + fwd_plan_occ_bytes(n_vox_total) +
@@ -132,7 +131,7 @@ __host__ inline bool fwd_plan_view(void *plan, int64_t n_vox_total, size_t plan_
     v->sub_iv = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->sub_pt = (int32_t *)p;                p += fwd_plan_sub_bytes(n_vox_total);
     v->heavy_list = (int32_t *)p;            p += fwd_plan_sub_bytes(n_vox_total);
-    v->sub_occ = (uint8_t *)p;               p += fwd_plan_occ_bytes(n_vox_total);
+    v->sub_mask = (uint32_t *)p;             p += fwd_plan_occ_bytes(n_vox_total);
     v->vox2iv = (int32_t *)p;                p += nv * 4;
     v->pos2iv = (int32_t *)p;                p += pc * 4;
     v->pt2vox = (int32_t *)p;                p += pc * 4;

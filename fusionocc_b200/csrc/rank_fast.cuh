@@ -94,20 +94,22 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
                       a.n_buckets < (int64_t)INT_MAX;
     if (fast) {
         const int b32 = (int)base;
-        // quarter-sub-tile occupancy of the four threads of a sub-tile (only meaningful when sub-tiles are aligned with
-        // the threads' 8-bucket groups, i.e. voxels per sample a multiple of 32)
-        const unsigned qm = __ballot_sync(0xffffffffu, mine != 0ull);
+        // occupancy mask of the sub-tile: eight buckets per thread, four threads per sub-tile (aligned with the threads'
+        // 8-bucket groups when voxels per sample is a multiple of 32; 0 = unknown otherwise)
+        unsigned m8 = 0;
+#pragma unroll
+        for (int j = 0; j < kScan2Items; ++j) m8 |= (c[j] > 0 ? 1u : 0u) << j;
+        unsigned m32 = m8;
+        m32 |= __shfl_down_sync(0xffffffffu, m8, 1) << 8;
+        m32 |= __shfl_down_sync(0xffffffffu, m8, 2) << 16;
+        m32 |= __shfl_down_sync(0xffffffffu, m8, 3) << 24;
         if (want_tiles) {
             const int sample = b32 / (int)a.vox_per_sample, vin = b32 - sample * (int)a.vox_per_sample;
             if ((vin & (kSub - 1)) == 0) {
                 const int u = sample * a.subs_per_sample + (vin >> kSubShift);
                 a.sub_iv[u] = (int)ne;
                 a.sub_pt[u] = (int)pts;
-                if (a.sub_occ) {
-                    const unsigned bits = (qm >> lane) & 0xFu;      // lane is a multiple of 4 here when V % 32 == 0
-                    a.sub_occ[u] = ((a.vox_per_sample & 31) == 0) ? (uint8_t)(((bits & 3u) ? 1 : 0) | ((bits & 12u) ? 2 : 0))
-                                                                  : (uint8_t)3;
-                }
+                if (a.sub_mask) a.sub_mask[u] = ((a.vox_per_sample & 31) == 0) ? m32 : 0u;
             }
         }
         int li = (int)ne - ne0;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
                         const int64_t u = sample * a.subs_per_sample + (vin >> kSubShift);
                         a.sub_iv[u] = (int)ne;
                         a.sub_pt[u] = (int)pts;
-                        if (a.sub_occ) a.sub_occ[u] = (uint8_t)3;
+                        if (a.sub_mask) a.sub_mask[u] = 0u;
                     }
                     if (++vin == a.vox_per_sample) { vin = 0; ++sample; }
                 }

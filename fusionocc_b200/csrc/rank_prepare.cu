@@ -425,7 +425,7 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
     // nothing downstream can index with uninitialised values (the backward reads pos2iv for every point)
     FO_CUDA(cudaMemsetAsync(pv.sub_iv, 0, (size_t)(n_subs + 1) * 4, stream));
     FO_CUDA(cudaMemsetAsync(pv.sub_pt, 0, (size_t)(n_subs + 1) * 4, stream));
-    FO_CUDA(cudaMemsetAsync(pv.sub_occ, 3, (size_t)n_subs + 1, stream));        // half-occupancy unknown
+    FO_CUDA(cudaMemsetAsync(pv.sub_mask, 0, ((size_t)n_subs + 1) * 4, stream));    // occupancy masks unknown
     if (n_points > 0) FO_CUDA(cudaMemsetAsync(pv.pos2iv, 0xFF, (size_t)n_points * 4, stream));
     init_fwd_header_kernel<<<1, 32, 0, stream>>>(pv.hdr, (int)n_subs, sps, (int)n_intervals);
     FO_LAUNCH_CHECK("init_fwd_header_kernel");
@@ -483,7 +483,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
             ChunkScratch sc = chunk_scratch_view(scratch, chunk_bound(NV), P);
             FO_CUDA(cudaMemsetAsync(scratch, 0, sc.zero_bytes, stream));
             FO_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), stream));
-            FO_CUDA(cudaMemsetAsync(pv.sub_occ, 3, (size_t)n_subs + 1, stream));  // half-occupancy unknown on this path
+            FO_CUDA(cudaMemsetAsync(pv.sub_mask, 0, ((size_t)n_subs + 1) * 4, stream));  // occupancy masks unknown on this path
             ChunkArgs ca;
             VoxArgs &va = ca.vox;
             va.coor = coor; va.n_points = P; va.points_per_sample = pps;
@@ -574,7 +574,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = pv.iv_vox;
     sa.bucket2iv = pv.vox2iv;
     sa.totals = counts_dev;
-    sa.sub_iv = pv.sub_iv; sa.sub_pt = pv.sub_pt; sa.sub_occ = nullptr; sa.vox_per_sample = n_vox; sa.subs_per_sample = sps;
+    sa.sub_iv = pv.sub_iv; sa.sub_pt = pv.sub_pt; sa.sub_mask = nullptr; sa.vox_per_sample = n_vox; sa.subs_per_sample = sps;
     sa.n_subs = (int)n_subs;
     sa.fwd_hdr = pv.hdr; sa.bwd_hdr = nullptr;
     sa.agg = ss.agg; sa.agg_group = ss.agg_group;
@@ -592,7 +592,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         ListArgs la;
         la.long_list = (int32_t *)((char *)slot + align_up(P * 4, 256)); la.long_cap = (int32_t)(P / 8 + 1);
         la.counts = ss.counter;
-        sa.sub_occ = pv.sub_occ;
+        sa.sub_mask = pv.sub_mask;
         // FO_RANK_FAST=2 (opt-in): (offset, interval id) pairs + a placement that turns pt2vox into pt2iv, so that the
         // backward plan needs no voxel -> interval gather.  Measured (profiles/r02_summary.md): backward -7 us, rank
         // precompute +6 us at batch 8 (+19 / -16 us at 512x1408): a wash with a backward, a loss without one.
@@ -613,7 +613,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         FO_CUDA(launch_pdl(kPdlRank, order2_kernel, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
         return FO_OK;
     }
-    FO_CUDA(cudaMemsetAsync(pv.sub_occ, 3, (size_t)n_subs + 1, stream));     // half-occupancy unknown on this path
+    FO_CUDA(cudaMemsetAsync(pv.sub_mask, 0, ((size_t)n_subs + 1) * 4, stream));   // occupancy masks unknown on this path
     FO_CUDA(launch_pdl(kPdlRank, scan_buckets_kernel, dim3(scan_blocks), dim3(kScanThreads), 0, stream, sa));
     FO_CUDA(launch_pdl(kPdlRank, place_kernel, dim3(grid_for(P, 256)), dim3(256), 0, stream, (const int32_t *)key,
                        (const int32_t *)slot, (const int32_t *)ss.cnt, P, (const int32_t *)nullptr, NV, ranks_depth));
@@ -701,7 +701,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     sa.iv_starts = interval_starts; sa.iv_lengths = interval_lengths; sa.iv_bucket = iv_bucket;
     sa.bucket2iv = nullptr;
     sa.totals = counts_dev;
-    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.sub_occ = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
+    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.sub_mask = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = nullptr;
     sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((n_buckets + kScanTile - 1) / kScanTile);
@@ -804,7 +804,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     sa.iv_starts = bv.starts; sa.iv_lengths = bv.lengths; sa.iv_bucket = bv.ids;
     sa.bucket2iv = nullptr;
     sa.totals = bv.hdr->totals;
-    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.sub_occ = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
+    sa.sub_iv = nullptr; sa.sub_pt = nullptr; sa.sub_mask = nullptr; sa.vox_per_sample = 1; sa.subs_per_sample = 0; sa.n_subs = 0;
     sa.fwd_hdr = nullptr; sa.bwd_hdr = bv.hdr;
     sa.agg = ss.agg; sa.agg_group = ss.agg_group;
     const int scan_blocks = (int)((n_feat_rows + kScanTile - 1) / kScanTile);
