@@ -479,7 +479,17 @@ __global__ void __launch_bounds__(kPix2Threads, FO_PIX2_MINB) bwd_pixel2_kernel(
 struct GatherTile {
     int ia, ni, my_v;
     int half;                       // 0: whole sub-tile staged (128-byte rows); 1 / 2: only its lower / upper 16 voxels (64-byte rows)
+    unsigned mask;                  // occupancy mask of the sub-tile (0: unknown, my_v holds the voxels read from iv_vox)
 };
+// position of the n-th (0-based) set bit of m, 32 if there is none: binary search on prefix population counts
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (__popc(m & ((1u << (pos + step)) - 1u)) <= n) pos += step;
+    return ((m >> pos) & 1u) && __popc(m & ((1u << pos) - 1u)) == n ? pos : 32;
+}
+
 template <int NACC, bool EXACT>
 __device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensorMap *tm, const CUtensorMap *tmh, float *stage,
                                              const unsigned bar, const int b, const int su, const int lane, GatherTile &t) {
@@ -506,9 +516,10 @@ __device__ __forceinline__ bool gather_issue(const GatherArgs &a, const CUtensor
     t.ia = ia;
     t.ni = min(ib - ia, kSub);
     t.my_v = -1;
+    t.mask = mask;
     if (mask != 0u) {
-        // interval l of the sub-tile is the l-th occupied voxel: no second, dependent index load
-        if (lane < t.ni) t.my_v = (int)__fns(mask, 0u, lane + 1);
+        // interval l of the sub-tile is its l-th occupied voxel: no second, dependent index load
+        if (lane < t.ni) t.my_v = nth_set_bit(mask, lane);
         if ((unsigned)t.my_v >= (unsigned)nv) t.my_v = -1;
     } else if (lane < t.ni) {
         const int vbase = (int)((int64_t)b * a.V) + v0;
@@ -528,7 +539,7 @@ __device__ __forceinline__ void gather_emit(const GatherArgs &a, const float *st
         const int vlo = t.half == 2 ? kSub / 2 : 0;
         for (int l = 0; l < t.ni; ++l, dst += C) {
             const int v = __shfl_sync(0xffffffffu, t.my_v, l) - vlo;
-            if ((unsigned)v >= (unsigned)(kSub / 2)) continue;       // warp-uniform (a voxel outside the staged half: never for a consistent plan)
+            if ((unsigned)v >= (unsigned)(kSub / 2)) continue;       // warp-uniform (never for a consistent plan)
 #pragma unroll
             for (int k = 0; k < NACC; ++k)
                 if (EXACT || lane + 32 * k < C) dst[32 * k] = lds_f32(sbase + swz64_off(lane + 32 * k, v));
@@ -582,7 +593,10 @@ struct PlanRideArgs {
     int32_t *ent_p, *ent_iv, *starts, *lengths, *ids;
     const int32_t *n_points_dev;
 };
-constexpr int kPlanPixPerWarp = 2;
+#ifndef FO_PLAN_PIX_PER_WARP
+#define FO_PLAN_PIX_PER_WARP 2
+#endif
+constexpr int kPlanPixPerWarp = FO_PLAN_PIX_PER_WARP;
 #ifndef FO_GRIDE_MINB
 #define FO_GRIDE_MINB 6      // 40 registers; plan CTAs sort in the stage area, so six CTAs fit the SM's shared memory
 #endif

@@ -93,8 +93,11 @@ def pack_calibration(sensor2ego, cam2imgs, post_rots, post_trans, bda):
     matrices carry the reference's bits; only the per-point products move into the kernel."""
     B, N = sensor2ego.shape[:2]
     f = lambda t: t.float()
-    inv_pr = torch.inverse(f(post_rots))
-    combine = f(sensor2ego)[:, :, :3, :3].matmul(torch.inverse(f(cam2imgs)[:, :, :3, :3]))
+    # torch.inverse == linalg.inv: the same factorisation kernels as inv_ex, plus a device->host read of the `info`
+    # flags (a pipeline stall per call).  inv_ex(check_errors=False) skips only that read: same bits, no sync.
+    inv = lambda m: torch.linalg.inv_ex(m, check_errors=False).inverse
+    inv_pr = inv(f(post_rots))
+    combine = f(sensor2ego)[:, :, :3, :3].matmul(inv(f(cam2imgs)[:, :, :3, :3]))
     cam = torch.cat((inv_pr.reshape(B, N, 9), f(post_trans).reshape(B, N, 3), combine.reshape(B, N, 9),
                      f(sensor2ego)[:, :, :3, 3].reshape(B, N, 3)), dim=2).reshape(B * N, 24).contiguous()
     has_t = bda.shape[-1] == 4
