@@ -541,7 +541,7 @@ def run_ours(args):
 
     # ---- e2e through the host-buffer entry
     hs = HostStep(ns, n_chunks=args.e2e_chunks)
-    for _ in range(2):
+    for _ in range(4):
         hs.step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -907,7 +907,8 @@ def main():
     ap.add_argument('--shape', default='base', choices=['base', 'native', 'stress'])
     ap.add_argument('--batch', type=int, default=8, help='samples per GPU per step')
     ap.add_argument('--e2e-steps', type=int, default=10)
-    ap.add_argument('--e2e-chunks', type=int, default=4)
+    ap.add_argument('--e2e-chunks', type=int, default=2,
+                    help='batch chunks of the host-buffer leg (profiles/e2e_probe.py: 2 chunks 13.8 ms, 4 chunks 14.0 ms, 8 chunks 14.1 ms per step)')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary legs (ref_cuda, python_api, c4, stress)')
