@@ -15,7 +15,9 @@
 // 4-byte store per point costs a 32-byte sector write: place 16.5 -> 34.4 us, order 29.7 -> 19.5 us — a net loss
 // (and 291 -> 352 us at 512x1408, where there are 2.5 points per voxel).  Also not kept: a slot-free count (reductions
 // without a return value in the voxelise pass, no 12 MB slot array; the placement draws positions with a returning
-// atomicAdd on the bucket offsets): rank precompute 95.7 -> 100.0 us at batch 8, 283.7 -> 291.9 us at 512x1408.
+// atomicAdd on the bucket offsets): rank precompute 95.7 -> 100.0 us at batch 8, 283.7 -> 291.9 us at 512x1408.  Nor the
+// scan's tile aggregates summed inside the voxelise pass (match.any per warp, one 64-bit atomic per distinct tile, no
+// tile_reduce launch): step 397.6 vs 397.7 us at batch 8, 939 vs 932 us at 512x1408.
 #pragma once
 
 #include "bucket_sort.cuh"
