@@ -652,8 +652,11 @@ def run_ours(args):
                 'pcie_probe': pcie,
                 'wire_floor_samples_per_s_per_gpu': (B / max(h2d_bytes / (pcie['h2d_GBps'] * 1e9), d2h_bytes / (pcie['d2h_GBps'] * 1e9))
                                              if isinstance(pcie, dict) and 'h2d_GBps' in pcie else None),
+                # uploads and downloads run at the same time: the box's both-directions throughput is the tighter bound
+                'both_ways_floor_samples_per_s_per_gpu': (B / ((h2d_bytes + d2h_bytes) / (pcie['both_GBps'] * 1e9))
+                                                          if isinstance(pcie, dict) and 'both_GBps' in pcie else None),
                 'note': 'every rank moves its own bytes through the host; the box-wide host<->device throughput, not '
-                        'the kernels, bounds this figure from two GPUs on'},
+                        'the kernels, bounds this figure (boxes of the pool differ: 89-97 GB/s both ways)'},
         'gpu_launches': KERNELS_PER_STEP * K,
         'clocks': clocks,
         'parity_checked': bool(isinstance(parity, dict) and parity.get('ok')),
