@@ -48,6 +48,7 @@ struct FwdArgs {
     int32_t sps;                    // sub-tiles per sample (host-known: saves a dependent load per CTA)
     int32_t check_flags;            // 0: the plan is trusted (FO_FWD_ASSUME_SORTED), skip the flag word
     int32_t store_evict_first;      // bulk-store write-out: L2 evict-first hint (sparse frusta; see forward_impl)
+    int32_t heavy_pts;              // dense sub-tile threshold of this plan (heavy_threshold(B, V))
 };
 
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(32, FO_FWD_MIN_CTAS) fwd_dense_kernel(FwdArgs 
         }
         return;
     }
-    if (a.front_y > 0 && pb - pa > kHeavyPts) return;    // a dense sub-tile: the front CTAs own it
+    if (a.front_y > 0 && pb - pa > a.heavy_pts) return;  // a dense sub-tile: the front CTAs own it
     if (EXACT) {
 #pragma unroll
         for (int i = 0; i < 8 * NACC; ++i) sts_zero4(sbase + 16u * lane + 512u * i);
@@ -486,6 +487,7 @@ int forward_impl(cudaStream_t stream, int32_t c, const float *depth, const float
     a.out_bstride = (int64_t)c_total * n_vox;
     a.out_rowstride = c_total;
     a.sps = sps; a.check_flags = (flags & FO_FWD_ASSUME_SORTED) ? 0 : 1;
+    a.heavy_pts = heavy_threshold(B, n_vox);
 
     // dense sub-tiles go to the front CTAs (contiguous (B,C,Z,Y,X) output only)
     const bool front_ok = out_layout == FO_LAYOUT_BCZYX && interval_starts != nullptr;
@@ -571,6 +573,6 @@ extern "C" void fo_compat_bev_pool_v2(int c, int n_intervals, const float *depth
     a.C = c; a.B = 1; a.V = INT_MAX - 1; a.out = out; a.hdr = nullptr; a.sub_pt = nullptr;
     a.sps = 0; a.check_flags = 0; a.out_bstride = 0; a.out_rowstride = c;
     a.sub_iv = nullptr; a.iv_vox = nullptr; a.heavy_list = nullptr; a.n_heavy = nullptr; a.front_y = 0;
-    a.store_evict_first = 0;
+    a.store_evict_first = 0; a.heavy_pts = kHeavyPts;
     fwd_scatter_kernel<FO_LAYOUT_BZYXC><<<grid_for((int64_t)n_intervals * 32, 256, 16), 256, 0, 0>>>(a, 0);
 }

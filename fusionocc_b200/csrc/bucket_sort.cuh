@@ -296,6 +296,7 @@ struct OrderArgs {
     const int32_t *sub_pt;
     int32_t n_subs;
     int32_t *heavy_list;
+    int32_t heavy_pts;          // dense sub-tile threshold (heavy_threshold(B, V))
     int32_t *heavy_n;           // zero-initialised
     int32_t *long_list;
     int32_t *long_count;        // zero-initialised; [0] = intervals of kLaneSortMax+1 .. kWarpSortMax points,
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(256) order_short_kernel(OrderArgs a) {
     const int stride = gridDim.x * blockDim.x;
     if (kForward && a.heavy_list != nullptr)
         for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.n_subs; u += stride)
-            if (a.sub_pt[u + 1] - a.sub_pt[u] > kHeavyPts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
+            if (a.sub_pt[u + 1] - a.sub_pt[u] > a.heavy_pts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         const int s = a.iv_starts[k], len = a.iv_lengths[k];
         if (len > kLaneSortMax) {

@@ -36,6 +36,14 @@ namespace fo {
 #define FO_HEAVY_PTS 256
 #endif
 constexpr int kHeavyPts     = FO_HEAVY_PTS;   // sub-tiles with more points are "dense": listed in the plan, split by the forward
+// The threshold is a function of the plan's identity (B, voxels per sample) only, so every entry point that lists or
+// skips dense sub-tiles derives the same value.  Long grids hide the serial chain of a 256..512-point sub-tile behind
+// the rest of the launch and prefer fewer front CTAs (measured, forward at batch 8: 512x1408 270.6 -> 260.8 us, stress
+// 642.7 -> 617.9 us, headline shape unchanged); short grids need the split (stress batch 2: 160 us at 256, 171 us at
+// 512; 512x1408 batch 1: 53 / 53 / 69 us at 256 / 512 / 1024).
+__host__ __device__ inline int heavy_threshold(int B, int64_t n_vox) {
+    return (int64_t)B * ((n_vox + 31) / 32) >= 131072 ? 2 * kHeavyPts : kHeavyPts;
+}
 constexpr int kSub          = 32;    // voxels per sub-tile (one warp)
 constexpr int kSubShift     = 5;
 #ifndef FO_TILE_THREADS

@@ -105,6 +105,7 @@ struct ChunkArgs {
     // outputs of the sort kernels
     int32_t *rb, *rd, *rf, *iv_starts, *iv_lengths;
     int32_t *sub_iv, *sub_pt, *heavy_list, *vox2iv, *iv_vox;
+    int32_t heavy_pts;           // dense sub-tile threshold (heavy_threshold(B, V))
     FwdPlanHeader *hdr;
     FastDiv dhw, hw;
     int32_t n_subs;
@@ -583,7 +584,7 @@ __device__ __forceinline__ void chunk_sort(const ChunkArgs &a, const int ch, int
                     if (lv0 + 4 * i4 + e < nv) a.vox2iv[v_lo + lv0 + 4 * i4 + e] = ivs[e];
             }
         }
-        if (prev - my_off > kHeavyPts) a.heavy_list[atomicAdd(a.hdr->fwd_heavy, 1)] = (int)u;
+        if (prev - my_off > a.heavy_pts) a.heavy_list[atomicAdd(a.hdr->fwd_heavy, 1)] = (int)u;
     }
     chunk_sync<NW>();
     // ---- order inside the voxels: 2..8 points one lane each (sorting network in registers) ...

@@ -267,6 +267,7 @@ struct Order2Args {
     const int32_t *sub_pt;      // dense sub-tile list of the forward plan
     int32_t n_subs;
     int32_t *heavy_list, *heavy_n;
+    int32_t heavy_pts;          // dense sub-tile threshold (heavy_threshold(B, V))
 };
 
 // One launch for the whole order pass: (1) queued long intervals, one warp each; (2) the forward plan's list of dense
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kSortThreads) order2_kernel(Order2Args a) {
     }
     if (a.heavy_list != nullptr)
         for (int u = gtid; u < a.n_subs; u += stride)
-            if (a.sub_pt[u + 1] - a.sub_pt[u] > kHeavyPts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
+            if (a.sub_pt[u + 1] - a.sub_pt[u] > a.heavy_pts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
     const int n = *a.n_intervals;
     for (int k = gtid; k < n; k += stride) {
         const int s = a.iv_starts[k], len = a.iv_lengths[k];

@@ -243,11 +243,11 @@ __global__ void __launch_bounds__(256) plan_from_intervals_kernel(
 // lists the dense sub-tiles of a plan built from caller-supplied intervals (the rank precompute does it inside
 // its order pass)
 __global__ void __launch_bounds__(256) heavy_queue_kernel(const int32_t *__restrict__ sub_pt, int n_subs,
-                                                          FwdPlanHeader *hdr, int32_t *heavy_list) {
+                                                          FwdPlanHeader *hdr, int32_t *heavy_list, int heavy_pts) {
     if (hdr->flags & kFlagUnsorted) return;               // sub_pt is not meaningful then
     const int stride = gridDim.x * blockDim.x;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_subs; u += stride)
-        if (sub_pt[u + 1] - sub_pt[u] > kHeavyPts) heavy_list[atomicAdd(hdr->fwd_heavy, 1)] = u;
+        if (sub_pt[u + 1] - sub_pt[u] > heavy_pts) heavy_list[atomicAdd(hdr->fwd_heavy, 1)] = u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -434,7 +434,8 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
         ranks_bev, interval_starts, interval_lengths, n_points, n_intervals, n_intervals_dev, n_vox,
         (int64_t)B * n_vox, sps, (int)n_subs, pv.hdr, pv.sub_iv, pv.sub_pt, pv.pos2iv, pv.iv_vox);
     FO_LAUNCH_CHECK("plan_from_intervals_kernel");
-    heavy_queue_kernel<<<grid_for(n_subs, 256, 4), 256, 0, stream>>>(pv.sub_pt, (int)n_subs, pv.hdr, pv.heavy_list);
+    heavy_queue_kernel<<<grid_for(n_subs, 256, 4), 256, 0, stream>>>(pv.sub_pt, (int)n_subs, pv.hdr, pv.heavy_list,
+                                                                     heavy_threshold(B, n_vox));
     FO_LAUNCH_CHECK("heavy_queue_kernel");
     return FO_OK;
 }
@@ -499,7 +500,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
             ca.rb = ranks_bev; ca.rd = ranks_depth; ca.rf = ranks_feat;
             ca.iv_starts = interval_starts; ca.iv_lengths = interval_lengths;
             ca.sub_iv = pv.sub_iv; ca.sub_pt = pv.sub_pt; ca.heavy_list = pv.heavy_list; ca.vox2iv = pv.vox2iv;
-            ca.iv_vox = pv.iv_vox; ca.hdr = pv.hdr;
+            ca.iv_vox = pv.iv_vox; ca.hdr = pv.hdr; ca.heavy_pts = heavy_threshold(B, n_vox);
             ca.dhw = make_fastdiv((uint32_t)(D * H * W)); ca.hw = make_fastdiv((uint32_t)(H * W));
             ca.n_subs = (int)n_subs;
             FO_CHECK_ARG((int64_t)B * N <= 65535, "B*N=%lld exceeds the grid bound", (long long)B * N);
@@ -610,6 +611,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         o2.iv_lengths = interval_lengths; o2.iv_bucket = pv.iv_vox; o2.n_intervals = counts_dev + 1;
         o2.l = la; o2.dhw = fd_dhw; o2.hw = fd_hw;
         o2.sub_pt = pv.sub_pt; o2.n_subs = (int32_t)n_subs; o2.heavy_list = pv.heavy_list; o2.heavy_n = pv.hdr->fwd_heavy;
+        o2.heavy_pts = heavy_threshold(B, n_vox);
         FO_CUDA(launch_pdl(kPdlRank, order2_kernel, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
         return FO_OK;
     }
@@ -623,6 +625,7 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
     oa.iv_bucket = pv.iv_vox; oa.n_intervals = counts_dev + 1;
     oa.ranks_feat = ranks_feat; oa.ranks_bev = ranks_bev;
     oa.sub_pt = pv.sub_pt; oa.n_subs = (int32_t)n_subs; oa.heavy_list = pv.heavy_list; oa.heavy_n = pv.hdr->fwd_heavy;
+    oa.heavy_pts = heavy_threshold(B, n_vox);
     oa.dhw = fd_dhw; oa.hw = fd_hw;
     oa.long_list = slot; oa.long_count = ss.counter;       // the slot array is dead after the placement
     oa.long_cap = (int32_t)P;
@@ -714,7 +717,7 @@ extern "C" int fo_rank_from_keys(fo_stream_t stream_, const int32_t *keys, int64
     OrderArgs oa;
     oa.sorted = order; oa.iv_starts = interval_starts; oa.iv_lengths = interval_lengths;
     oa.iv_bucket = iv_bucket; oa.n_intervals = counts_dev + 1;
-    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr;
+    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr; oa.heavy_pts = kHeavyPts;
     oa.ranks_feat = nullptr; oa.ranks_bev = sorted_keys;
     oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)n_points;
@@ -818,7 +821,7 @@ extern "C" int fo_bwd_plan_build(fo_stream_t stream_, const int32_t *ranks_depth
     OrderArgs oa;
     oa.sorted = bv.pos; oa.iv_starts = bv.starts; oa.iv_lengths = bv.lengths; oa.iv_bucket = nullptr;
     oa.n_intervals = &bv.hdr->n_bwd_intervals;
-    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr;
+    oa.sub_pt = nullptr; oa.n_subs = 0; oa.heavy_list = nullptr; oa.heavy_n = nullptr; oa.heavy_pts = kHeavyPts;
     oa.ranks_feat = nullptr; oa.ranks_bev = nullptr; oa.dhw = make_fastdiv(1); oa.hw = make_fastdiv(1);
     oa.long_list = bv.slot; oa.long_count = ss.counter; oa.long_cap = (int32_t)bv.cap;
     order_short_kernel<false><<<grid_for(n_feat_rows, 256, 8), 256, 0, stream>>>(oa);
