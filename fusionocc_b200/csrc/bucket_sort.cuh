@@ -321,6 +321,21 @@ __device__ __forceinline__ void sort8(int (&v)[8]) {
     cswap(v[3], v[4]);
 }
 
+// Batcher's odd-even merge sort for 16 keys (63 comparators; verified exhaustively with the 0-1 principle)
+__device__ __forceinline__ void sort16(int (&v)[16]) {
+    cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[1], v[2]); cswap(v[4], v[5]);
+    cswap(v[6], v[7]); cswap(v[4], v[6]); cswap(v[5], v[7]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[2], v[6]);
+    cswap(v[2], v[4]); cswap(v[1], v[5]); cswap(v[3], v[7]); cswap(v[3], v[5]); cswap(v[1], v[2]); cswap(v[3], v[4]);
+    cswap(v[5], v[6]); cswap(v[8], v[9]); cswap(v[10], v[11]); cswap(v[8], v[10]); cswap(v[9], v[11]); cswap(v[9], v[10]);
+    cswap(v[12], v[13]); cswap(v[14], v[15]); cswap(v[12], v[14]); cswap(v[13], v[15]); cswap(v[13], v[14]); cswap(v[8], v[12]);
+    cswap(v[10], v[14]); cswap(v[10], v[12]); cswap(v[9], v[13]); cswap(v[11], v[15]); cswap(v[11], v[13]); cswap(v[9], v[10]);
+    cswap(v[11], v[12]); cswap(v[13], v[14]); cswap(v[0], v[8]); cswap(v[4], v[12]); cswap(v[4], v[8]); cswap(v[2], v[10]);
+    cswap(v[6], v[14]); cswap(v[6], v[10]); cswap(v[2], v[4]); cswap(v[6], v[8]); cswap(v[10], v[12]); cswap(v[1], v[9]);
+    cswap(v[5], v[13]); cswap(v[5], v[9]); cswap(v[3], v[11]); cswap(v[7], v[15]); cswap(v[7], v[11]); cswap(v[3], v[5]);
+    cswap(v[7], v[9]); cswap(v[11], v[13]); cswap(v[1], v[2]); cswap(v[3], v[4]); cswap(v[5], v[6]); cswap(v[7], v[8]);
+    cswap(v[9], v[10]); cswap(v[11], v[12]); cswap(v[13], v[14]);
+}
+
 constexpr int kLaneSortMax = 8;   // intervals up to this length are ordered by one lane in registers
 constexpr int kWarpSortMax = 128; // ... up to this length by one warp in registers; longer ones by a whole CTA
 

@@ -28,10 +28,13 @@ constexpr int kScan2Threads = 256;
 constexpr int kScan2Items   = kScanTile / kScan2Threads;      // 8 buckets per thread
 static_assert(kScan2Items == 8 && kScanTile == 2048, "scan2 is written for 2048-bucket tiles, 256 threads x 8");
 
+constexpr int kMidSortMax = 16;  // intervals of kLaneSortMax+1 .. kMidSortMax points: one lane each, 16-key network
 struct ListArgs {
-    int32_t *long_list;      // intervals of kLaneSortMax+1 .. kWarpSortMax points from the front, longer ones from the END
-    int32_t *counts;         // zero-initialised: [1] long (front), [2] long (end)
-    int32_t long_cap;
+    int32_t *long_list;      // intervals of kMidSortMax+1 .. kWarpSortMax points from the front, longer ones from the END
+    int32_t *mid_list;       // intervals of kLaneSortMax+1 .. kMidSortMax points
+    int32_t *counts;         // zero-initialised: [0] mid, [1] long (front), [2] long (end)
+    int32_t long_cap, mid_cap;
+    int32_t mid_max;         // kMidSortMax, or kLaneSortMax to switch the mid queue off (FO_RANK_MID=0)
     int2 *ofiv;              // optional [n_buckets]: (point offset, interval id) of every bucket in ONE 8-byte entry — the
                              // placement then fetches both with a single gather (instead of cnt in place + bucket2iv)
 };
@@ -40,14 +43,15 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
     __shared__ unsigned long long s_warp[kScan2Threads / 32];
     __shared__ unsigned long long s_red[kScan2Threads / 32];
     __shared__ int s_st[kScanTile], s_ln[kScanTile], s_vx[kScanTile];
-    __shared__ int s_q[kScanTile / 8];       // tile-local queue of long intervals (> 8 points each, 2048 buckets)
-    __shared__ int s_qn, s_qbase;
+    __shared__ int s_q[kScanTile / 8];       // tile-local queue of long intervals (> 16 points each, 2048 buckets)
+    __shared__ int s_m[kScanTile / 8];       // ... of the 9..16-point intervals
+    __shared__ int s_qn, s_qbase, s_mn, s_mbase;
     pdl_wait();
     pdl_launch();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     const int64_t base = (int64_t)tile * kScanTile + (int64_t)tid * kScan2Items;
-    if (tid == 0) s_qn = 0;
+    if (tid == 0) { s_qn = 0; s_mn = 0; }
 
     unsigned long long pre = 0;
     const int g0 = tile / kScanGroup;
@@ -201,10 +205,17 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
         a.iv_lengths[ne0 + i] = len;
         if (a.iv_bucket) a.iv_bucket[ne0 + i] = s_vx[i];
         if (len > kLaneSortMax) {
-            if (len <= kWarpSortMax) {
+            if (len <= l.mid_max) {
+                const int at = atomicAdd(&s_mn, 1);
+                if (at < kScanTile / 8) s_m[at] = ne0 + i;
+                else {                                   // a tile with more than 256 such intervals: straight to the global queue
+                    const int g = atomicAdd(l.counts + 0, 1);
+                    if (g < l.mid_cap) l.mid_list[g] = ne0 + i;
+                }
+            } else if (len <= kWarpSortMax) {
                 const int at = atomicAdd(&s_qn, 1);
                 if (at < kScanTile / 8) s_q[at] = ne0 + i;
-                else {                                   // a tile with more than 256 long intervals: straight to the global queue
+                else {
                     const int g = atomicAdd(l.counts + 1, 1);
                     if (g < l.long_cap) l.long_list[g] = ne0 + i;
                 }
@@ -215,11 +226,14 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
         }
     }
     __syncthreads();
-    const int nl = min(s_qn, kScanTile / 8);
+    const int nl = min(s_qn, kScanTile / 8), nm = min(s_mn, kScanTile / 8);
     if (tid == 0 && nl > 0) s_qbase = atomicAdd(l.counts + 1, nl);
+    if (tid == 32 && nm > 0) s_mbase = atomicAdd(l.counts + 0, nm);
     __syncthreads();
     for (int i = tid; i < nl; i += kScan2Threads)
         if (s_qbase + i < l.long_cap) l.long_list[s_qbase + i] = s_q[i];
+    for (int i = tid; i < nm; i += kScan2Threads)
+        if (s_mbase + i < l.mid_cap) l.mid_list[s_mbase + i] = s_m[i];
 }
 
 // Placement with the interval id riding along: sorted[offset + slot] = p, and the point's voxel id in key[] is
@@ -272,6 +286,7 @@ struct Order2Args {
 
 // One launch for the whole order pass: (1) queued long intervals, one warp each; (2) the forward plan's list of dense
 // sub-tiles; (3) every interval of up to kLaneSortMax points, one lane each; (4) very long intervals, one CTA each.
+template <bool MID>   // MID: the 9..16-point queue exists (dense frusta); without it the kernel needs 40 instead of 48 registers
 __global__ void __launch_bounds__(kSortThreads) order2_kernel(Order2Args a) {
     __shared__ int s_sort[kSortSmemCta];
     pdl_wait();
@@ -295,6 +310,24 @@ __global__ void __launch_bounds__(kSortThreads) order2_kernel(Order2Args a) {
     if (a.heavy_list != nullptr)
         for (int u = gtid; u < a.n_subs; u += stride)
             if (a.sub_pt[u + 1] - a.sub_pt[u] > a.heavy_pts) a.heavy_list[atomicAdd(a.heavy_n, 1)] = u;
+    // 9..16-point intervals: one lane each, 16-key network in registers (a warp per such interval cost ~200 warp
+    // instructions each: 83 k of them at 512x1408 batch 8)
+    const int n_mid = MID ? min(a.l.counts[0], a.l.mid_cap) : 0;
+    for (int i = gtid; MID && i < n_mid; i += stride) {
+        const int k = a.l.mid_list[i];
+        const int s = a.iv_starts[k], len = a.iv_lengths[k], bucket = a.iv_bucket[k];
+        int v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
+        sort16(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < len) {
+                a.sorted[s + j] = v[j];
+                a.ranks_feat[s + j] = feat_row_of(v[j], a.dhw, a.hw);
+                a.ranks_bev[s + j] = bucket;
+            }
+    }
     const int n = *a.n_intervals;
     for (int k = gtid; k < n; k += stride) {
         const int s = a.iv_starts[k], len = a.iv_lengths[k];

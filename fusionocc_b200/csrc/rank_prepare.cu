@@ -442,9 +442,9 @@ extern "C" int fo_fwd_plan_build(fo_stream_t stream_, const int32_t *ranks_bev, 
 
 extern "C" size_t fo_rank_prepare_scratch_bytes(int64_t n_points_total, int64_t n_voxels_total) {
     if (n_points_total < 0 || n_voxels_total < 0) return 0;
-    // counters + aggregates | slot[P] | long-interval queue of the order pass [P/8 + 1] | (offset, interval) pairs [NV]
+    // counters + aggregates | slot[P] | two interval queues of the order pass [P/8 + 1 each] | (offset, interval) pairs [NV]
     const size_t legacy = bucket_zero_bytes(n_voxels_total) + (size_t)align_up(n_points_total * 4, 256) +
-                          (size_t)align_up((n_points_total / 8 + 1) * 4, 256) + (size_t)align_up(n_voxels_total * 8, 256);
+                          2 * (size_t)align_up((n_points_total / 8 + 1) * 4, 256) + (size_t)align_up(n_voxels_total * 8, 256);
     const size_t chunked = chunk_scratch_view(nullptr, chunk_bound(n_voxels_total), n_points_total).total_bytes;
     return legacy > chunked ? legacy : chunked;
 }
@@ -592,12 +592,21 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         // long-interval queue: lives behind the slot array (both are live until the placement has run)
         ListArgs la;
         la.long_list = (int32_t *)((char *)slot + align_up(P * 4, 256)); la.long_cap = (int32_t)(P / 8 + 1);
+        la.mid_list = (int32_t *)((char *)la.long_list + align_up(((int64_t)P / 8 + 1) * 4, 256)); la.mid_cap = (int32_t)(P / 8 + 1);
         la.counts = ss.counter;
+        {
+            // 9..16-point intervals one lane each for dense frusta (more points than voxels: 512x1408 rank precompute
+            // 283.4 -> 269.7 us at batch 8; at the headline shape there are too few of them to pay for the registers,
+            // 95.8 -> 98.0 us); FO_RANK_MID=0/1 forces it off / on (A/B)
+            const char *me = getenv("FO_RANK_MID");
+            const bool mid = (me && *me) ? atoi(me) != 0 : P > NV;
+            la.mid_max = mid ? kMidSortMax : kLaneSortMax;
+        }
         sa.sub_mask = pv.sub_mask;
         // FO_RANK_FAST=2 (opt-in): (offset, interval id) pairs + a placement that turns pt2vox into pt2iv, so that the
         // backward plan needs no voxel -> interval gather.  Measured (profiles/r02_summary.md): backward -7 us, rank
         // precompute +6 us at batch 8 (+19 / -16 us at 512x1408): a wash with a backward, a loss without one.
-        la.ofiv = fast >= 2 ? (int2 *)((char *)la.long_list + align_up(((int64_t)P / 8 + 1) * 4, 256)) : nullptr;
+        la.ofiv = fast >= 2 ? (int2 *)((char *)la.mid_list + align_up(((int64_t)P / 8 + 1) * 4, 256)) : nullptr;
         if (la.ofiv) sa.bucket2iv = nullptr;
         FO_CUDA(launch_pdl(kPdlRank, scan_buckets2_kernel, dim3(scan_blocks), dim3(kScan2Threads), 0, stream, sa, la));
         if (la.ofiv)
@@ -612,7 +621,8 @@ int rank_prepare_impl(cudaStream_t stream, const float *coor, const CalibArgs *c
         o2.l = la; o2.dhw = fd_dhw; o2.hw = fd_hw;
         o2.sub_pt = pv.sub_pt; o2.n_subs = (int32_t)n_subs; o2.heavy_list = pv.heavy_list; o2.heavy_n = pv.hdr->fwd_heavy;
         o2.heavy_pts = heavy_threshold(B, n_vox);
-        FO_CUDA(launch_pdl(kPdlRank, order2_kernel, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
+        if (la.mid_max > kLaneSortMax) FO_CUDA(launch_pdl(kPdlRank, order2_kernel<true>, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
+        else FO_CUDA(launch_pdl(kPdlRank, order2_kernel<false>, dim3(sm_count() * 16), dim3(kSortThreads), 0, stream, o2));
         return FO_OK;
     }
     FO_CUDA(cudaMemsetAsync(pv.sub_mask, 0, ((size_t)n_subs + 1) * 4, stream));   // occupancy masks unknown on this path

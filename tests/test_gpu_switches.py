@@ -31,6 +31,8 @@ SWITCHES = [
     {'FO_BWD_RIDE': '2'},
     {'FO_BWD_HALF': '0'},
     {'FO_VOX_IMPL': '0'},
+    {'FO_RANK_MID': '0'},
+    {'FO_RANK_MID': '1'},
 ]
 NAMES = sorted({k for s in SWITCHES for k in s})
 
