@@ -374,8 +374,14 @@ __device__ __forceinline__ void pixel_warp(const PixelArgs &a, float *wsm, const
     for (int base = 0; base < maxlen; base += kRecCap) {
         const int cnt = min(kRecCap, maxlen - base);             // warp-uniform
         __syncwarp();                                            // the previous chunk is done with rec / recp
-        // ---- phase 1: records of this chunk
-        constexpr int RB = 4;
+        // ---- phase 1: records of this chunk.  RB batches of LPR entries per lane group = the whole chunk in ONE pass:
+        //      all entry loads, then all depth loads (two dependent round trips per chunk; with RB = 4 at C = 32 a
+        //      50-point pixel took two passes = four round trips)
+#ifndef FO_PIX_RB
+        constexpr int RB = kRecCap / LPR;
+#else
+        constexpr int RB = FO_PIX_RB;
+#endif
         for (int i0 = 0; i0 < cnt; i0 += LPR * RB) {
             int p[RB], row[RB];
 #pragma unroll
