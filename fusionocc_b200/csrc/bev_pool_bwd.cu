@@ -303,7 +303,10 @@ __global__ void __launch_bounds__(kPixThreads) bwd_pixel_kernel(PixelArgs a) {
 // =================================================================================================
 constexpr int kPix2Threads = 128;            // threads per CTA of the multi-pixel kernel (short CTAs: finer tail)
 constexpr int kPix2Warps   = kPix2Threads / 32;
-constexpr int kRecCap      = 64;             // records of one pixel staged per chunk (longer pixels take several chunks)
+#ifndef FO_REC_CAP
+#define FO_REC_CAP 64
+#endif
+constexpr int kRecCap      = FO_REC_CAP;     // records of one pixel staged per chunk (longer pixels take several chunks); multiple of 32
 
 struct Pixel2Cfg {
     int32_t tile_stride;   // floats per row of the per-warp tile rows[32][tile_stride]: C + 4 or C + 8 (conflict-free LDS.128)

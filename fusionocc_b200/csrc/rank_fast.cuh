@@ -42,7 +42,7 @@ struct ListArgs {
 __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a, ListArgs l) {
     __shared__ unsigned long long s_warp[kScan2Threads / 32];
     __shared__ unsigned long long s_red[kScan2Threads / 32];
-    __shared__ int s_st[kScanTile], s_ln[kScanTile], s_vx[kScanTile];
+    __shared__ int4 s_iv[kScanTile];         // (first point, points, voxel, -) of the tile's intervals, in interval order
     __shared__ int s_q[kScanTile / 8];       // tile-local queue of long intervals (> 16 points each, 2048 buckets)
     __shared__ int s_m[kScanTile / 8];       // ... of the 9..16-point intervals
     __shared__ int s_qn, s_qbase, s_mn, s_mbase;
@@ -120,18 +120,17 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
                 if (a.sub_mask) a.sub_mask[u] = ((a.vox_per_sample & 31) == 0) ? m32 : 0u;
             }
         }
+        // branch-free walk: one predicated 16-byte store per occupied bucket, the running sums advance unconditionally
+        // (an empty bucket adds zero points) — the eight divergent branches per thread were half of this kernel's
+        // instructions (ncu source view)
         int li = (int)ne - ne0;
 #pragma unroll
         for (int j = 0; j < kScan2Items; ++j) {
             o[j] = (int)pts;
             iv[j] = ne0 + li;
-            if (c[j] > 0) {
-                s_st[li] = (int)pts;
-                s_ln[li] = c[j];
-                s_vx[li] = b32 + j;
-                pts += (unsigned)c[j];
-                ++li;
-            }
+            if (c[j] > 0) s_iv[li] = make_int4((int)pts, c[j], b32 + j, 0);
+            pts += (unsigned)c[j];
+            li += c[j] > 0 ? 1 : 0;
         }
         ne = (unsigned)(ne0 + li);
     } else {
@@ -154,9 +153,7 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
                 }
                 if (c[j] > 0) {
                     const int li = (int)ne - ne0;
-                    s_st[li] = (int)pts;
-                    s_ln[li] = c[j];
-                    s_vx[li] = (int)v;
+                    s_iv[li] = make_int4((int)pts, c[j], (int)v, 0);
                     pts += (unsigned)c[j];
                     ++ne;
                 }
@@ -200,10 +197,11 @@ __global__ void __launch_bounds__(kScan2Threads) scan_buckets2_kernel(ScanArgs a
     __syncthreads();
     // compact per-interval outputs: full lines; classification of the intervals that need ordering
     for (int i = tid; i < n_tile; i += kScan2Threads) {
-        const int len = s_ln[i];
-        a.iv_starts[ne0 + i] = s_st[i];
+        const int4 e = s_iv[i];
+        const int len = e.y;
+        a.iv_starts[ne0 + i] = e.x;
         a.iv_lengths[ne0 + i] = len;
-        if (a.iv_bucket) a.iv_bucket[ne0 + i] = s_vx[i];
+        if (a.iv_bucket) a.iv_bucket[ne0 + i] = e.z;
         if (len > kLaneSortMax) {
             if (len <= l.mid_max) {
                 const int at = atomicAdd(&s_mn, 1);
@@ -329,10 +327,14 @@ __global__ void __launch_bounds__(kSortThreads) order2_kernel(Order2Args a) {
             }
     }
     const int n = *a.n_intervals;
+    // one lane per short interval; the next interval's (start, length, voxel) are fetched while this one is ordered
+    // (two dependent round trips per iteration otherwise: interval record, then its points)
+    int ns = 0, nlen = 0, nb = 0;
+    if (gtid < n) { ns = a.iv_starts[gtid]; nlen = a.iv_lengths[gtid]; nb = a.iv_bucket[gtid]; }
     for (int k = gtid; k < n; k += stride) {
-        const int s = a.iv_starts[k], len = a.iv_lengths[k];
+        const int s = ns, len = nlen, bucket = nb;
+        if (k + stride < n) { ns = a.iv_starts[k + stride]; nlen = a.iv_lengths[k + stride]; nb = a.iv_bucket[k + stride]; }
         if (len > kLaneSortMax) continue;
-        const int bucket = a.iv_bucket[k];
         int v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (j < len) ? a.sorted[s + j] : INT_MAX;
