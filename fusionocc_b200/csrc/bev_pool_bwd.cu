@@ -555,12 +555,22 @@ __device__ __forceinline__ void gather_emit(const GatherArgs &a, const float *st
         }
         return;
     }
-    for (int l = 0; l < t.ni; ++l, dst += C) {
-        const int v = __shfl_sync(0xffffffffu, t.my_v, l);
-        if (v < 0) continue;                         // warp-uniform
+    // four intervals per trip: the shuffles, the staged reads and the row stores of a trip are independent chains
+    for (int l0 = 0; l0 < t.ni; l0 += 4, dst += 4 * C) {
+        int v[4];
+        float x[4][NACC];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k)
-            if (EXACT || lane + 32 * k < C) dst[32 * k] = lds_f32(sbase + swz_off(lane + 32 * k, v));
+        for (int u = 0; u < 4; ++u) v[u] = __shfl_sync(0xffffffffu, t.my_v, (l0 + u) & 31);   // lanes >= ni hold -1
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NACC; ++k)
+                x[u][k] = (v[u] >= 0 && (EXACT || lane + 32 * k < C)) ? lds_f32(sbase + swz_off(lane + 32 * k, v[u])) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NACC; ++k)
+                if (v[u] >= 0 && l0 + u < t.ni && (EXACT || lane + 32 * k < C)) dst[u * C + 32 * k] = x[u][k];
     }
 }
 
