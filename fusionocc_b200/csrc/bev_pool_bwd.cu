@@ -608,6 +608,9 @@ struct PlanRideArgs {
     int32_t D, HW, n_rows;
     int32_t n_plan_ctas, n_gather_ctas, gu;   // gu = gather CTAs per sample
     int32_t plan_first;                       // 1: the plan CTAs are the first blocks of the grid instead of interleaved
+    int32_t small;                            // 1: (grid size) x (plan CTAs) < 2^31: the interleave map in 32-bit arithmetic
+    FastDiv div_T;                            // division by the grid size (the 64-bit divisions of the map were ~100
+                                              // instructions for EVERY warp of the grid: 16 M of the kernel's 72 M)
     BwdPlanHeader *hdr;
     int32_t *ent_p, *ent_iv, *starts, *lengths, *ids;
     const int32_t *n_points_dev;
@@ -633,8 +636,18 @@ __global__ void __launch_bounds__(256, FO_GRIDE_MINB) bwd_gather_plan_kernel(Gat
     int *s_cmp = reinterpret_cast<int *>(gsm) + warp * (32 * R);
     const long long T = (long long)p.n_plan_ctas + p.n_gather_ctas;
     const int bid = blockIdx.x;
-    const int plans_before = p.plan_first ? min(bid, p.n_plan_ctas) : (int)(((long long)bid * p.n_plan_ctas) / T);
-    const bool is_plan = p.plan_first ? bid < p.n_plan_ctas : (int)(((long long)(bid + 1) * p.n_plan_ctas) / T) > plans_before;
+    int plans_before;
+    bool is_plan;
+    if (p.plan_first) {
+        plans_before = min(bid, p.n_plan_ctas);
+        is_plan = bid < p.n_plan_ctas;
+    } else if (p.small) {
+        plans_before = (int)fastdiv((uint32_t)bid * (uint32_t)p.n_plan_ctas, p.div_T);
+        is_plan = (int)fastdiv((uint32_t)(bid + 1) * (uint32_t)p.n_plan_ctas, p.div_T) > plans_before;
+    } else {
+        plans_before = (int)(((long long)bid * p.n_plan_ctas) / T);
+        is_plan = (int)(((long long)(bid + 1) * p.n_plan_ctas) / T) > plans_before;
+    }
     if (is_plan) {
         if (plans_before == 0 && threadIdx.x == 0) {
             p.hdr->n_bwd_intervals = p.n_rows;
@@ -949,6 +962,11 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
                     pr.fhdr = pv.hdr; pr.pt2vox = pv.pt2vox; pr.vox2iv = pv.vox2iv; pr.D = D; pr.HW = req->hw; pr.n_rows = (int)n_feat_rows;
                     pr.gu = gu; pr.n_gather_ctas = gu * B;
                     pr.n_plan_ctas = (int)((n_feat_rows + 8 * kPlanPixPerWarp - 1) / (8 * kPlanPixPerWarp));
+                    {
+                        const int64_t T = (int64_t)pr.n_plan_ctas + pr.n_gather_ctas;
+                        pr.small = (T + 1) * pr.n_plan_ctas < (1ll << 31) ? 1 : 0;
+                        pr.div_T = make_fastdiv((uint32_t)(T < 1 ? 1 : (T > 0x7fffffff ? 0x7fffffff : T)));
+                    }
                     const int ride = bwd_ride_choice();
                     pr.plan_first = ride == 2 || (ride < 0 && pr.n_gather_ctas <= 8 * FO_GRIDE_MINB * sm_count()) ? 1 : 0;
                     pr.hdr = bv.hdr; pr.ent_p = bv.ent_p; pr.ent_iv = bv.ent_iv; pr.starts = bv.starts;
