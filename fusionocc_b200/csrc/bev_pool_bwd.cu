@@ -609,6 +609,7 @@ struct PlanRideArgs {
     int32_t n_plan_ctas, n_gather_ctas, gu;   // gu = gather CTAs per sample
     int32_t plan_first;                       // 1: the plan CTAs are the first blocks of the grid instead of interleaved
     int32_t small;                            // 1: (grid size) x (plan CTAs) < 2^31: the interleave map in 32-bit arithmetic
+    FastDiv div_gu;                           // division by gu
     FastDiv div_T;                            // division by the grid size (the 64-bit divisions of the map were ~100
                                               // instructions for EVERY warp of the grid: 16 M of the kernel's 72 M)
     BwdPlanHeader *hdr;
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(256, FO_GRIDE_MINB) bwd_gather_plan_kernel(Gat
         return;
     }
     const int gi = bid - plans_before;
-    const int b = gi / p.gu, blk = gi - b * p.gu;
+    const int b = (int)fastdiv((uint32_t)gi, p.div_gu), blk = gi - b * p.gu;
     const int C = EXACT ? 32 * NACC : a.C;
     const unsigned stage_bytes = ((unsigned)C * 128u + 1023u) & ~1023u;
     unsigned char *base = (unsigned char *)(((uintptr_t)gsm + 1023) & ~(uintptr_t)1023);
@@ -965,6 +966,7 @@ int backward_impl(cudaStream_t stream, int32_t c, const float *out_grad, int32_t
                     {
                         const int64_t T = (int64_t)pr.n_plan_ctas + pr.n_gather_ctas;
                         pr.small = (T + 1) * pr.n_plan_ctas < (1ll << 31) ? 1 : 0;
+                        pr.div_gu = make_fastdiv((uint32_t)gu);
                         pr.div_T = make_fastdiv((uint32_t)(T < 1 ? 1 : (T > 0x7fffffff ? 0x7fffffff : T)));
                     }
                     const int ride = bwd_ride_choice();

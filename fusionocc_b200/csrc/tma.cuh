@@ -67,12 +67,14 @@ inline int make_voxel_tmap(CUtensorMap *tm, const float *base, int64_t V, int32_
 // shared-memory address lives at byte offset  c*128 + (((v >> 2) ^ (c & 7)) << 4) + (v & 3)*4.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned swz_off(int c, int v) {
-    return ((unsigned)c << 7) + ((((unsigned)v >> 2) ^ ((unsigned)c & 7u)) << 4) + (((unsigned)v & 3u) << 2);
+    // = c*128 + (((v >> 2) ^ (c & 7)) << 4) + (v & 3)*4: the XOR only touches the chunk bits of v, so it can be applied
+    // to v itself with the row's constant (c & 7) << 2 — two instructions per access for a lane with a fixed row
+    return ((unsigned)c << 7) + (((unsigned)v ^ (((unsigned)c & 7u) << 2)) << 2);
 }
 
 // Half box (16 voxels, 64-byte rows, 64-byte swizzle: address bits [5:4] ^= bits [8:7]): element (c, v), v < 16
 __device__ __forceinline__ unsigned swz64_off(int c, int v) {
-    return ((unsigned)c << 6) + ((((unsigned)v >> 2) ^ (((unsigned)c >> 1) & 3u)) << 4) + (((unsigned)v & 3u) << 2);
+    return ((unsigned)c << 6) + (((unsigned)v ^ ((((unsigned)c >> 1) & 3u) << 2)) << 2);
 }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
